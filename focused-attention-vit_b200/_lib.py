@@ -1,0 +1,68 @@
+"""ctypes binding of libfavit_b200.so — the C-ABI declared in include/favit.h.
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.  Nothing here (or
+anywhere in this package) imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfavit_b200.so")
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_GELU, EPI_DGELU_MUL = 0, 1, 2
+
+_lib = None
+
+_vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+
+_SIGS = {
+    "favit_version": ([], _i),
+    "favit_device_cc": ([], _i),
+    "favit_last_error": ([], C.c_char_p),
+    "favit_launch_count": ([], _u64),
+    "favit_mhla_attn_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
+    "favit_mhla_attn_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f,
+                             _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
+    "favit_linear_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp], _i),
+    "favit_linear_dgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp], _i),
+    "favit_linear_wgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp], _i),
+    "favit_gemm_bf16_raw": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_assign": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "favit_sppp_pool_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_pool_bwd": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite against include/favit.h)."""
+    return sorted(_SIGS)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python focused-attention-vit_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the favit ops)")
+        l = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(l, name)       # AttributeError if the symbol is not exported
+            fn.argtypes = args
+            fn.restype = res
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().favit_last_error().decode(errors="replace")
+        kind = {1: "bad argument", 2: "unsupported", 3: "CUDA error", 4: "workspace"}.get(rc, f"status {rc}")
+        raise RuntimeError(f"{what}: {kind}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().favit_launch_count())

@@ -1,0 +1,174 @@
+// C-ABI entry points of the linear layers: forward, data gradient, weight/bias gradient.
+// They replace nn.Linear and its autograd at /root/reference/models/mhla.py:100 (qkv), :158 (proj) and, as the
+// "next" row, the MLP linears of models/vit.py:107-139.  bf16 runs on the tcgen05 kernel (gemm_tcgen05.cu), fp32 on
+// the SIMT parity kernel (gemm_simt.cu).
+#include "favit_common.cuh"
+#include "gemm_tcgen05.h"
+
+namespace favit {
+namespace {
+
+// db[n] (+)= sum_m dy[m,n].  One thread owns 8 consecutive columns (one 16-byte load per row for bf16), a CTA
+// walks a strip of rows, partial sums are combined through shared memory and one atomic per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, int M, int N,
+                                                     int64_t ld, int rows_per_cta) {
+  __shared__ float s_part[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const bool vec = (c0 + 8 <= N) && (ld % 8 == 0) && ((uintptr_t)dy % 16 == 0);
+  if (c0 < N) {
+    if (vec) {
+      int r = r0 + warp;
+      for (; r + 24 < r1; r += 32) {
+        float f[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(dy + (int64_t)(r + 8 * u) * ld + c0, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += f[u][e];
+      }
+      for (; r < r1; r += 8) {
+        float f[8];
+        load8(dy + (int64_t)r * ld + c0, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    } else {
+      for (int r = r0 + warp; r < r1; r += 8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c0 + e < N) acc[e] += Elem<T>::ld(dy + (int64_t)r * ld + c0 + e);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_part[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w][threadIdx.x];
+    atomicAdd(db + c, s);
+  }
+}
+
+template <typename T>
+int launch_colsum(const void* dy, float* db, int M, int N, int64_t ld, cudaStream_t st) {
+  const int col_blocks = ceil_div(N, 256);
+  int row_blocks = max(1, min(ceil_div(M, 64), (4 * num_sms()) / col_blocks));
+  const int rows_per_cta = ceil_div(ceil_div(M, row_blocks), 8) * 8;
+  row_blocks = ceil_div(M, rows_per_cta);
+  colsum_kernel<T><<<dim3(col_blocks, row_blocks), 256, 0, st>>>((const T*)dy, db, M, N, ld, rows_per_cta);
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+int check_dims(const char* who, int M, int N, int K) {
+  FAVIT_CHECK_ARG(M > 0 && N > 0 && K > 0, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
+  return FAVIT_OK;
+}
+
+}  // namespace
+}  // namespace favit
+
+using namespace favit;
+
+extern "C" int favit_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                void* preact_out, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                                int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
+                                int epilogue, favit_stream stream) {
+  if (int rc = check_dims("linear_fwd", M, N, K)) return rc;
+  FAVIT_CHECK_ARG(x && w && y, "linear_fwd: null x/w/y");
+  FAVIT_CHECK_ARG(epilogue == FAVIT_EPI_NONE || epilogue == FAVIT_EPI_GELU, "linear_fwd: bad epilogue %d", epilogue);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FAVIT_F32) {
+    FAVIT_CHECK_ARG(y_dtype == FAVIT_F32 && (!residual || res_dtype == FAVIT_F32),
+                    "linear_fwd: the fp32 path is fp32 end to end");
+    return gemm_simt_launch((const float*)x, (const float*)w, (float*)y, bias, nullptr, (float*)preact_out,
+                            (const float*)residual, ldres, M, N, K, ldx, 1, ldw, 1, ldy, epilogue, 1, 0, st);
+  }
+  FAVIT_CHECK_ARG(dtype == FAVIT_BF16, "linear_fwd: bad dtype");
+  tc::Epilogue e;
+  e.c = y; e.ldc = ldy; e.c_dtype = y_dtype;
+  e.bias = bias;
+  e.residual = residual; e.ldres = ldres; e.res_dtype = res_dtype;
+  e.aux_out = preact_out; e.ldaux = ldy;
+  e.act = epilogue;
+  return tc::gemm_bf16(x, 0, ldx, w, 0, ldw, M, N, K, e, 0, 0, st);
+}
+
+extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, int M, int N, int K,
+                                  int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype, favit_dtype dx_dtype,
+                                  int epilogue, favit_stream stream) {
+  if (int rc = check_dims("linear_dgrad", M, N, K)) return rc;
+  FAVIT_CHECK_ARG(dy && w && dx, "linear_dgrad: null dy/w/dx");
+  FAVIT_CHECK_ARG(epilogue == FAVIT_EPI_NONE || (epilogue == FAVIT_EPI_DGELU_MUL && preact),
+                  "linear_dgrad: bad epilogue %d", epilogue);
+  cudaStream_t st = (cudaStream_t)stream;
+  // dX[m,k] = sum_n dY[m,n] W[n,k]: output M x K, reduction over N; W is stored [reduction][out] (MN-major B)
+  if (dtype == FAVIT_F32) {
+    FAVIT_CHECK_ARG(dx_dtype == FAVIT_F32, "linear_dgrad: the fp32 path is fp32 end to end");
+    return gemm_simt_launch((const float*)dy, (const float*)w, (float*)dx, nullptr, (const float*)preact, nullptr,
+                            nullptr, 0, M, K, N, lddy, 1, 1, ldw, lddx, epilogue, 1, 0, st);
+  }
+  FAVIT_CHECK_ARG(dtype == FAVIT_BF16, "linear_dgrad: bad dtype");
+  tc::Epilogue e;
+  e.c = dx; e.ldc = lddx; e.c_dtype = dx_dtype;
+  e.aux = preact; e.ldaux = lddx;
+  e.act = epilogue;
+  return tc::gemm_bf16(dy, 0, lddy, w, 1, ldw, M, K, N, e, 0, 0, st);
+}
+
+extern "C" int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
+                                  int64_t lddy, int64_t ldx, int64_t lddw, favit_dtype dtype, int accumulate,
+                                  favit_stream stream) {
+  if (int rc = check_dims("linear_wgrad", M, N, K)) return rc;
+  FAVIT_CHECK_ARG(dy && x && dw, "linear_wgrad: null dy/x/dw");
+  FAVIT_CHECK_ARG(dtype == FAVIT_F32 || dtype == FAVIT_BF16, "linear_wgrad: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    if (lddw == K) {
+      FAVIT_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+    } else {
+      FAVIT_CHECK_CUDA(cudaMemset2DAsync(dw, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
+    }
+    if (db) FAVIT_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+  }
+  // dW[n,k] = sum_m dY[m,n] X[m,k]: output N x K, reduction over M; both operands stored [reduction][out]
+  int rc;
+  if (dtype == FAVIT_F32) {
+    const int tiles = ceil_div(N, 64) * ceil_div(K, 64);
+    int splits = max(1, min(ceil_div(M, 256), (2 * num_sms()) / max(tiles, 1)));
+    rc = gemm_simt_launch((const float*)dy, (const float*)x, dw, nullptr, nullptr, nullptr, nullptr, 0, N, K, M, 1,
+                          lddy, 1, ldx, lddw, FAVIT_EPI_NONE, splits, 1, st);
+  } else {
+    tc::Epilogue e;
+    e.c = dw; e.ldc = lddw; e.c_dtype = FAVIT_F32;
+    e.accumulate = 1; e.split_ok = 1;
+    rc = tc::gemm_bf16(dy, 1, lddy, x, 1, ldx, N, K, M, e, 0, 0, st);
+  }
+  if (rc) return rc;
+  if (db) {
+    if (dtype == FAVIT_F32) return launch_colsum<float>(dy, db, M, N, lddy, st);
+    return launch_colsum<__nv_bfloat16>(dy, db, M, N, lddy, st);
+  }
+  return FAVIT_OK;
+}
+
+extern "C" int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb,
+                                   void* c, int64_t ldc, favit_dtype c_dtype, int M, int N, int K, int bn, int splits,
+                                   favit_stream stream) {
+  if (int rc = check_dims("gemm_bf16_raw", M, N, K)) return rc;
+  FAVIT_CHECK_ARG(a && b && c, "gemm_bf16_raw: null pointer");
+  tc::Epilogue e;
+  e.c = c; e.ldc = ldc; e.c_dtype = c_dtype;
+  e.split_ok = (splits > 1) ? 1 : 0;
+  return tc::gemm_bf16(a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, M, N, K, e, bn, splits, (cudaStream_t)stream);
+}

@@ -1,0 +1,387 @@
+"""torch.library registration of the favit C-ABI kernels (namespace ``favit::``).
+
+Every op allocates its outputs with torch on the input's device, passes raw device pointers and the current
+torch stream to libfavit_b200.so, and never touches the CPU oracle.  Differentiable ops (`linear`,
+`mhla_attn`, `sppp_pool`) carry their backward through `register_autograd`, itself made of favit ops.
+
+Reference spans replaced (under /root/reference): models/mhla.py:100,158 (linears), :109-154 (window attention),
+models/sppp.py:91-128 (assignment), :192-223 + models/sppp_mhla.py:286-300 (pooling).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+_TD = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+
+
+def _dt(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"favit ops take float32 or bfloat16 tensors, got {t.dtype}") from None
+
+
+def _cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("favit ops run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """2-D view whose last dim is contiguous (leading dimension = stride(0))."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+# ------------------------------------------------------------------------------------------------
+# linear layers
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("favit::linear_fwd", mutates_args=())
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], gelu: bool,
+               out_dtype: torch.dtype, save_preact: bool) -> Tuple[Tensor, Tensor]:
+    """y = act(x @ w.T + bias) + residual.  x [M,K], w [N,K] (same dtype), bias fp32 [N].  Returns (y, preact);
+    preact is empty unless gelu and save_preact."""
+    _cuda(x, w, bias, residual)
+    x, w = _rowmajor(x), _rowmajor(w)
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or w.dtype != x.dtype:
+        raise ValueError(f"linear_fwd: x {tuple(x.shape)} {x.dtype} vs w {tuple(w.shape)} {w.dtype}")
+    if bias is not None:
+        bias = bias.float().contiguous()
+    y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    pre = torch.empty((M, N) if (gelu and save_preact) else (0,), dtype=x.dtype, device=x.device)
+    if residual is not None:
+        residual = _rowmajor(residual)
+    if M == 0:
+        return y, pre
+    rc = L.lib().favit_linear_fwd(
+        _p(x), _p(w), _p(bias), _p(residual), _p(y), _p(pre) if pre.numel() else None, M, N, K, _ld(x), _ld(w), N,
+        _ld(residual) if residual is not None else 0, _dt(x), _DT[out_dtype],
+        _dt(residual) if residual is not None else L.F32, L.EPI_GELU if gelu else L.EPI_NONE, _stream())
+    L.check(rc, "favit_linear_fwd")
+    return y, pre
+
+
+@linear_fwd.register_fake
+def _(x, w, bias, residual, gelu, out_dtype, save_preact):
+    M, N = x.shape[0], w.shape[0]
+    return (x.new_empty((M, N), dtype=out_dtype),
+            x.new_empty((M, N) if (gelu and save_preact) else (0,)))
+
+
+@torch.library.custom_op("favit::linear_dgrad", mutates_args=())
+def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype) -> Tensor:
+    """dx = dy @ w  (* gelu'(preact)).  dy [M,N], w [N,K]."""
+    _cuda(dy, w, preact)
+    dy, w = _rowmajor(dy), _rowmajor(w)
+    M, N = dy.shape
+    K = w.shape[1]
+    if w.shape[0] != N or w.dtype != dy.dtype:
+        raise ValueError(f"linear_dgrad: dy {tuple(dy.shape)} {dy.dtype} vs w {tuple(w.shape)} {w.dtype}")
+    dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
+    if preact is not None:
+        preact = preact.contiguous()
+    if M == 0:
+        return dx
+    rc = L.lib().favit_linear_dgrad(_p(dy), _p(w), _p(preact), _p(dx), M, N, K, _ld(dy), _ld(w), K, _dt(dy),
+                                    _DT[out_dtype], L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _stream())
+    L.check(rc, "favit_linear_dgrad")
+    return dx
+
+
+@linear_dgrad.register_fake
+def _(dy, w, preact, out_dtype):
+    return dy.new_empty((dy.shape[0], w.shape[1]), dtype=out_dtype)
+
+
+@torch.library.custom_op("favit::linear_wgrad", mutates_args=())
+def linear_wgrad(dy: Tensor, x: Tensor, want_bias: bool) -> Tuple[Tensor, Tensor]:
+    """dw[N,K] = dy.T @ x (fp32), db[N] = column sums of dy (fp32; empty unless want_bias)."""
+    _cuda(dy, x)
+    dy, x = _rowmajor(dy), _rowmajor(x)
+    M, N = dy.shape
+    K = x.shape[1]
+    if x.shape[0] != M or x.dtype != dy.dtype:
+        raise ValueError(f"linear_wgrad: dy {tuple(dy.shape)} {dy.dtype} vs x {tuple(x.shape)} {x.dtype}")
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    db = torch.empty((N,) if want_bias else (0,), dtype=torch.float32, device=dy.device)
+    if M == 0:
+        return dw.zero_(), db.zero_()
+    rc = L.lib().favit_linear_wgrad(_p(dy), _p(x), _p(dw), _p(db) if want_bias else None, M, N, K, _ld(dy), _ld(x), K,
+                                    _dt(dy), 0, _stream())
+    L.check(rc, "favit_linear_wgrad")
+    return dw, db
+
+
+@linear_wgrad.register_fake
+def _(dy, x, want_bias):
+    N, K = dy.shape[1], x.shape[1]
+    return (dy.new_empty((N, K), dtype=torch.float32), dy.new_empty((N,) if want_bias else (0,), dtype=torch.float32))
+
+
+@torch.library.custom_op("favit::linear", mutates_args=())
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """nn.Linear forward in x's dtype: x [..., K] (fp32 or bf16), weight [N,K] / bias [N] of any float dtype
+    (fp32 master parameters are cast to the compute dtype here; their gradients come back in fp32)."""
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+    y, _ = linear_fwd(x2, w, bias, None, False, x.dtype, False)
+    return y.view(*x.shape[:-1], weight.shape[0])
+
+
+@linear.register_fake
+def _(x, weight, bias):
+    return x.new_empty((*x.shape[:-1], weight.shape[0]))
+
+
+def _linear_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+    ctx.bias_dtype = bias.dtype if bias is not None else None
+
+
+def _linear_backward(ctx, dy):
+    x, weight = ctx.saved_tensors
+    K = x.shape[-1]
+    N = weight.shape[0]
+    dy2 = dy.reshape(-1, N)
+    if dy2.dtype != x.dtype:
+        dy2 = dy2.to(x.dtype)
+    x2 = x.reshape(-1, K)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        dx = linear_dgrad(dy2, w, None, x.dtype).view(x.shape)
+    if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        dw, db = linear_wgrad(dy2, x2, ctx.has_bias)
+        dw = dw.to(weight.dtype)
+        db = db.to(ctx.bias_dtype) if ctx.has_bias else None
+    return dx, dw, db
+
+
+linear.register_autograd(_linear_backward, setup_context=_linear_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# MHLA window attention core
+# ------------------------------------------------------------------------------------------------
+def _qkv_args(qkv: Tensor):
+    B, N, three, H, hd = qkv.shape
+    if three != 3 or not qkv.is_contiguous():
+        raise ValueError("mhla_attn: qkv must be a contiguous [B, N, 3, H, hd] tensor (the packed qkv GEMM output)")
+    es = qkv.element_size()
+    base = qkv.data_ptr()
+    return B, N, H, hd, base, base + H * hd * es, base + 2 * H * hd * es, N * 3 * H * hd, 3 * H * hd, hd
+
+
+@torch.library.custom_op("favit::mhla_attn_fwd", mutates_args=())
+def mhla_attn_fwd(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """qkv [B,N,3,H,hd] -> (out [B,N,H*hd], lse fp32 [B,H,N]).  mask: uint8 [B,N,N] or None."""
+    _cuda(qkv, mask)
+    B, N, H, hd, q, k, v, sb, sn, sh = _qkv_args(qkv)
+    out = torch.empty((B, N, H * hd), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    if mask is not None and (mask.dtype != torch.uint8 or mask.shape != (B, N, N) or not mask.is_contiguous()):
+        raise ValueError("mhla_attn: mask must be a contiguous uint8 [B,N,N] tensor")
+    if B * N == 0:
+        return out, lse
+    rc = L.lib().favit_mhla_attn_fwd(q, k, v, _p(mask), _p(out), _p(lse), B, H, N, hd, window, float(hd) ** -0.5,
+                                     sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
+    L.check(rc, "favit_mhla_attn_fwd")
+    return out, lse
+
+
+@mhla_attn_fwd.register_fake
+def _(qkv, window, mask):
+    B, N, _, H, hd = qkv.shape
+    return qkv.new_empty((B, N, H * hd)), qkv.new_empty((B, H, N), dtype=torch.float32)
+
+
+@torch.library.custom_op("favit::mhla_attn_bwd", mutates_args=())
+def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: int, mask: Optional[Tensor]) -> Tensor:
+    """Gradient of mhla_attn_fwd w.r.t. the packed qkv: returns dqkv [B,N,3,H,hd]."""
+    _cuda(qkv, out, lse, dout, mask)
+    B, N, H, hd, q, k, v, sb, sn, sh = _qkv_args(qkv)
+    dout = dout.contiguous()
+    if dout.dtype != qkv.dtype:
+        dout = dout.to(qkv.dtype)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    if B * N == 0:
+        return dqkv
+    es = qkv.element_size()
+    dq = dqkv.data_ptr()
+    rc = L.lib().favit_mhla_attn_bwd(q, k, v, _p(mask), _p(out), _p(lse), _p(dout), dq, dq + H * hd * es,
+                                     dq + 2 * H * hd * es, _p(delta), B, H, N, hd, window, float(hd) ** -0.5,
+                                     sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
+    L.check(rc, "favit_mhla_attn_bwd")
+    return dqkv
+
+
+@mhla_attn_bwd.register_fake
+def _(qkv, out, lse, dout, window, mask):
+    return torch.empty_like(qkv)
+
+
+@torch.library.custom_op("favit::mhla_attn", mutates_args=())
+def mhla_attn(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """Differentiable window attention: (out [B,N,D], lse)."""
+    return mhla_attn_fwd(qkv, window, mask)
+
+
+@mhla_attn.register_fake
+def _(qkv, window, mask):
+    B, N, _, H, hd = qkv.shape
+    return qkv.new_empty((B, N, H * hd)), qkv.new_empty((B, H, N), dtype=torch.float32)
+
+
+def _attn_setup(ctx, inputs, output):
+    qkv, window, mask = inputs
+    out, lse = output
+    ctx.save_for_backward(qkv, out, lse, mask if mask is not None else torch.empty(0))
+    ctx.window = window
+    ctx.has_mask = mask is not None
+    ctx.set_materialize_grads(False)
+
+
+def _attn_backward(ctx, dout, dlse):
+    qkv, out, lse, mask = ctx.saved_tensors
+    if dlse is not None:
+        raise RuntimeError("mhla_attn: gradients through the log-sum-exp output are not supported")
+    if dout is None:
+        return torch.zeros_like(qkv), None, None
+    return mhla_attn_bwd(qkv, out, lse, dout, ctx.window, mask if ctx.has_mask else None), None, None
+
+
+mhla_attn.register_autograd(_attn_backward, setup_context=_attn_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# SPPP
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("favit::sppp_assign", mutates_args=())
+def sppp_assign(labels: Tensor, patch_size: int, img_size: int, r_cap: int) -> List[Tensor]:
+    """labels int64 [B,H,W] -> [dom i64 [B,P], slot i32 [B,P], num_slots i32 [B], counts i32 [B,r_cap],
+    slot_label i64 [B,r_cap], offsets i32 [B,r_cap+1], order i32 [B,P]]  (bit-exact with sppp.py:91-128)."""
+    _cuda(labels)
+    if labels.dtype != torch.int64 or labels.dim() != 3:
+        raise ValueError("sppp_assign: labels must be an int64 [B,H,W] tensor")
+    labels = labels.contiguous()
+    B, Hh, Ww = labels.shape
+    g = img_size // patch_size
+    P = g * g
+    dev = labels.device
+    dom = torch.empty((B, P), dtype=torch.int64, device=dev)
+    slot = torch.empty((B, P), dtype=torch.int32, device=dev)
+    num_slots = torch.empty((B,), dtype=torch.int32, device=dev)
+    counts = torch.empty((B, r_cap), dtype=torch.int32, device=dev)
+    slot_label = torch.empty((B, r_cap), dtype=torch.int64, device=dev)
+    offsets = torch.empty((B, r_cap + 1), dtype=torch.int32, device=dev)
+    order = torch.empty((B, P), dtype=torch.int32, device=dev)
+    if B * P:
+        rc = L.lib().favit_sppp_assign(_p(labels), B, Hh, Ww, patch_size, g, _p(dom), _p(slot), _p(num_slots),
+                                       _p(counts), _p(slot_label), _p(offsets), _p(order), r_cap, _stream())
+        L.check(rc, "favit_sppp_assign")
+    return [dom, slot, num_slots, counts, slot_label, offsets, order]
+
+
+@sppp_assign.register_fake
+def _(labels, patch_size, img_size, r_cap):
+    B = labels.shape[0]
+    P = (img_size // patch_size) ** 2
+    i32, i64 = torch.int32, torch.int64
+    return [labels.new_empty((B, P), dtype=i64), labels.new_empty((B, P), dtype=i32),
+            labels.new_empty((B,), dtype=i32), labels.new_empty((B, r_cap), dtype=i32),
+            labels.new_empty((B, r_cap), dtype=i64), labels.new_empty((B, r_cap + 1), dtype=i32),
+            labels.new_empty((B, P), dtype=i32)]
+
+
+@torch.library.custom_op("favit::sppp_pool_fwd", mutates_args=())
+def sppp_pool_fwd(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int,
+                  out_dtype: torch.dtype) -> Tensor:
+    _cuda(x, order, offsets, num_slots)
+    x = x.contiguous()
+    B, P, D = x.shape
+    r_cap = offsets.shape[1] - 1
+    out = torch.empty((B, R, D), dtype=out_dtype, device=x.device)
+    if out.numel():
+        rc = L.lib().favit_sppp_pool_fwd(_p(x), _dt(x), _p(order), _p(offsets), _p(num_slots), _p(out), _DT[out_dtype],
+                                         B, P, R, D, r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_fwd")
+    return out
+
+
+@sppp_pool_fwd.register_fake
+def _(x, order, offsets, num_slots, R, out_dtype):
+    return x.new_empty((x.shape[0], R, x.shape[2]), dtype=out_dtype)
+
+
+@torch.library.custom_op("favit::sppp_pool_bwd", mutates_args=())
+def sppp_pool_bwd(dout: Tensor, slot: Tensor, counts: Tensor, dx_dtype: torch.dtype) -> Tensor:
+    _cuda(dout, slot, counts)
+    dout = dout.contiguous()
+    B, R, D = dout.shape
+    P = slot.shape[1]
+    r_cap = counts.shape[1]
+    dx = torch.empty((B, P, D), dtype=dx_dtype, device=dout.device)
+    if dx.numel():
+        rc = L.lib().favit_sppp_pool_bwd(_p(dout), _dt(dout), _p(slot), _p(counts), _p(dx), _DT[dx_dtype], B, P, R, D,
+                                         r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_bwd")
+    return dx
+
+
+@sppp_pool_bwd.register_fake
+def _(dout, slot, counts, dx_dtype):
+    return dout.new_empty((dout.shape[0], slot.shape[1], dout.shape[2]), dtype=dx_dtype)
+
+
+@torch.library.custom_op("favit::sppp_pool", mutates_args=())
+def sppp_pool(x: Tensor, slot: Tensor, counts: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor,
+              R: int) -> Tensor:
+    """Differentiable batched segment mean: x [B,P,D] -> fp32 [B,R,D] (the reference's output is always fp32,
+    sppp.py:198)."""
+    return sppp_pool_fwd(x, order, offsets, num_slots, R, torch.float32)
+
+
+@sppp_pool.register_fake
+def _(x, slot, counts, order, offsets, num_slots, R):
+    return x.new_empty((x.shape[0], R, x.shape[2]), dtype=torch.float32)
+
+
+def _pool_setup(ctx, inputs, output):
+    x, slot, counts = inputs[0], inputs[1], inputs[2]
+    ctx.save_for_backward(slot, counts)
+    ctx.x_dtype = x.dtype
+
+
+def _pool_backward(ctx, dout):
+    slot, counts = ctx.saved_tensors
+    return sppp_pool_bwd(dout, slot, counts, ctx.x_dtype), None, None, None, None, None, None
+
+
+sppp_pool.register_autograd(_pool_backward, setup_context=_pool_setup)

@@ -1,0 +1,156 @@
+/*
+ * favit.h — C ABI of the B200-native MHLA + SPPP hot path (libfavit_b200.so).
+ *
+ * The reference (zser092/Focused-Attention-ViT) is pure Python/PyTorch and has no FFI; the "interface"
+ * each entry point replaces is therefore a span of eager PyTorch code inside a reference method, cited
+ * per function below as <file>:<lines> under /root/reference.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to call these.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer on the current device;
+ *   - the caller allocates every output / workspace and passes the stream to launch on;
+ *   - return 0 on success, a favit_status otherwise; favit_last_error() returns a thread-local
+ *     message; nothing throws, allocates device memory or synchronises the stream;
+ *   - kernels are stateless and re-entrant; the library is sm_100a only.
+ */
+#ifndef FAVIT_H_
+#define FAVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { FAVIT_F32 = 0, FAVIT_BF16 = 1 } favit_dtype;
+
+typedef enum {
+  FAVIT_OK = 0,
+  FAVIT_ERR_ARG = 1,          /* bad argument (null pointer, negative size, misalignment) */
+  FAVIT_ERR_UNSUPPORTED = 2,  /* valid request this build does not implement             */
+  FAVIT_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed                      */
+  FAVIT_ERR_WORKSPACE = 4     /* workspace too small                                      */
+} favit_status;
+
+typedef enum {
+  FAVIT_EPI_NONE = 0,       /* C = A.B (+bias)                                   */
+  FAVIT_EPI_GELU = 1,       /* C = gelu(A.B + bias)  (erf form, nn.GELU default)   */
+  FAVIT_EPI_DGELU_MUL = 2   /* C = (A.B) * gelu'(aux)   aux has C's shape/ld      */
+} favit_epilogue;
+
+typedef void* favit_stream;   /* cudaStream_t */
+
+int favit_version(void);
+/* compute capability of the current device, major*10+minor (100 on B200); < 0 on error */
+int favit_device_cc(void);
+const char* favit_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t favit_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MHLA windowed attention core — replaces models/mhla.py:109-154 (index table, both gathers, scaled
+ * scores, mask, softmax, PV) and never materialises the [B,H,N,W,hd] windows.
+ *
+ *   out[b,i,h,:] = sum_j m(i,j) exp(s_ij - lse) v[b,j,h,:],  s_ij = scale * q[b,i,h,:].k[b,j,h,:]
+ *   m(i,j) = window multiplicity of mhla.py:63-81 (band + duplicated edge index).
+ *
+ * q,k,v: element (b,i,h,d) at ptr + b*stride_b + i*stride_n + h*stride_h + d   (strides in elements;
+ *        the packed [B,N,3,H,hd] output of the qkv GEMM is read in place).
+ * mask:  NULL or uint8 [B,N,N], 0 = masked (mhla.py:136-143).
+ * out:   [B,N,H,hd] contiguous (== [B,N,D], the layout proj consumes, mhla.py:157); lse: fp32 [B,H,N].
+ * window may be even only when N <= window (the reference raises otherwise, mhla.py:83).
+ * dropout_p > 0 applies attention-probability dropout (mhla.py:147) with a counter-based generator
+ * keyed by (seed, b, h, i, slot); backward regenerates the same keep-mask.
+ * ---------------------------------------------------------------------------------------------- */
+int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, const uint8_t* mask,
+                        void* out, float* lse,
+                        int B, int H, int N, int hd, int window, float scale,
+                        int64_t stride_b, int64_t stride_n, int64_t stride_h,
+                        favit_dtype dtype, float dropout_p, uint64_t seed, favit_stream stream);
+
+/* Backward of the above (the reference relies on autograd: gather -> scatter_add_, bmm, softmax).
+ * dout: [B,N,H,hd] contiguous.  dq,dk,dv use the same strides as q,k,v (written in place into a packed
+ * dqkv buffer).  delta: fp32 workspace [B,H,N]. */
+int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, const uint8_t* mask,
+                        const void* out, const float* lse, const void* dout,
+                        void* dq, void* dk, void* dv, float* delta,
+                        int B, int H, int N, int hd, int window, float scale,
+                        int64_t stride_b, int64_t stride_n, int64_t stride_h,
+                        favit_dtype dtype, float dropout_p, uint64_t seed, favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers of the block — replace nn.Linear forward/backward at models/mhla.py:100 (qkv) and
+ * :158 (proj) (the latent projection :105-106 is folded into their weights by the host side) and,
+ * for the "next" row, the MLP (models/vit.py:107-139, models/mhla.py:197-203).
+ * dtype FAVIT_BF16: tcgen05.mma tiles, TMEM accumulators, TMA-fed (operands bf16, fp32 accumulate).
+ * dtype FAVIT_F32 : SIMT FFMA tiles (parity path for the 1e-4 bar; everything fp32).
+ * Row-major, leading dimensions in elements.  bias / db / dw are always fp32.
+ *
+ * favit_linear_fwd : Y[M,N] = act(X[M,K] . W[N,K]^T + bias[N]) + residual[M,N]
+ *      epilogue FAVIT_EPI_NONE or FAVIT_EPI_GELU; with GELU and preact_out != NULL the pre-activation
+ *      is also written (dtype = `dtype`, leading dimension ldy) for the backward pass.
+ *      bias, residual, preact_out may be NULL.  y_dtype/res_dtype select fp32 or bf16 for Y / residual
+ *      (the fp32 residual stream of a bf16 block); they must be FAVIT_F32 when dtype is FAVIT_F32.
+ * favit_linear_dgrad: dX[M,K] = dY[M,N] . W[N,K]   (epilogue FAVIT_EPI_DGELU_MUL: * gelu'(preact[M,K]),
+ *      preact has dX's leading dimension)
+ * favit_linear_wgrad: dW[N,K] (+)= dY[M,N]^T . X[M,K]  and, when db != NULL, db[N] (+)= column sums of dY.
+ *      accumulate == 0 overwrites (the call zero-fills first), != 0 adds to the existing values.
+ *      Split-K partial sums are combined with fp32 atomics, so the last bits may vary between runs.
+ * ---------------------------------------------------------------------------------------------- */
+int favit_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                     void* preact_out, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                     int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
+                     int epilogue, favit_stream stream);
+
+int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, int M, int N, int K,
+                       int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype, favit_dtype dx_dtype,
+                       int epilogue, favit_stream stream);
+
+int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
+                       int64_t lddy, int64_t ldx, int64_t lddw, favit_dtype dtype, int accumulate,
+                       favit_stream stream);
+
+/* Test / tuning hook: C[M,N] = A.B^T through the tcgen05 kernel with explicit operand storage
+ * (a_mn / b_mn: 0 = reduction dimension contiguous, 1 = M/N dimension contiguous), tile width
+ * (0 = auto, 64, 128, 256) and split-K factor (0 = auto).  C fp32 or bf16. */
+int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb, void* c,
+                        int64_t ldc, favit_dtype c_dtype, int M, int N, int K, int bn, int splits,
+                        favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SPPP patch -> superpixel assignment — replaces PatchToSuperpixelMapper.map_patches,
+ * models/sppp.py:91-128, for a whole batch in one call (the reference loops per image,
+ * models/sppp_mhla.py:286-297).
+ *
+ * labels: int64 [B, img_h, img_w] (row stride img_w).  grid = img_size / patch (trailing pixels are
+ * ignored like sppp.py:102).  P = grid*grid.
+ * dom[B,P]      int64  dominant label of each patch (most frequent, ties -> smallest id, sppp.py:117-120)
+ * slot[B,P]     int32  pooled-row index = rank of the label's first appearance in raster patch order
+ *                      (dict insertion order, sppp.py:123-126)
+ * num_slots[B]  int32  R of each image (may exceed r_cap: rows >= r_cap are then not written)
+ * counts[B,r_cap] int32, slot_label[B,r_cap] int64, offsets[B,r_cap+1] int32, order[B,P] int32:
+ *                      CSR of patches per slot, ascending patch id inside a slot (== the dict's lists)
+ * All integer outputs are bit-exact with the reference.
+ * ---------------------------------------------------------------------------------------------- */
+int favit_sppp_assign(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
+                      int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
+                      int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap,
+                      favit_stream stream);
+
+/* SuperpixelPooling.pool('mean') — replaces models/sppp.py:192-223 + the per-image loop/stack at
+ * models/sppp_mhla.py:286-300.  x[B,P,D] (x_dtype) -> out[B,R,D] (out_dtype; the reference always
+ * produces fp32, sppp.py:198).  Rows r >= num_slots[b] are zero-filled. */
+int favit_sppp_pool_fwd(const void* x, favit_dtype x_dtype, const int32_t* order, const int32_t* offsets,
+                        const int32_t* num_slots, void* out, favit_dtype out_dtype,
+                        int B, int P, int R, int D, int r_cap, favit_stream stream);
+
+/* Backward: dx[b,p,:] = dout[b,slot[b,p],:] / counts[b,slot[b,p]]. */
+int favit_sppp_pool_bwd(const void* dout, favit_dtype dout_dtype, const int32_t* slot, const int32_t* counts,
+                        void* dx, favit_dtype dx_dtype, int B, int P, int R, int D, int r_cap,
+                        favit_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAVIT_H_ */

@@ -1,0 +1,94 @@
+"""GPU parity: favit::mhla_attn (window attention core, fwd + bwd) against the CPU oracle's closed form, which is
+itself pinned to the reference by tests/test_oracle_golden.py.  Tolerances: 1e-4 relative fp32, 2e-2 bf16."""
+import pytest
+import torch
+
+import oracle
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, H, N, hd, W, mask
+    (2, 3, 65, 64, 7, False),     # C1 shape
+    (1, 2, 10, 64, 7, False),
+    (2, 2, 5, 64, 7, False),      # N < W: every row pads with N-1 / 0
+    (1, 1, 3, 64, 7, False),
+    (2, 2, 1, 64, 7, False),      # N = 1
+    (1, 3, 12, 32, 3, False),
+    (1, 1, 6, 16, 1, False),      # W = 1
+    (2, 2, 40, 64, 15, False),
+    (1, 2, 17, 64, 31, False),    # C2 tokens with a window wider than the sequence
+    (1, 12, 197, 64, 7, False),   # C4 shape, one image
+    (2, 2, 10, 64, 7, True),
+    (1, 2, 3, 64, 4, False),      # even window allowed when N <= W
+    (1, 2, 4, 128, 4, False),
+]
+
+
+def _run(B, H, N, hd, W, use_mask, dtype):
+    from favit_b200 import ops
+    torch.manual_seed(B * 1000 + N * 10 + W)
+    qkv = torch.randn(B, N, 3, H, hd)
+    dout = torch.randn(B, N, H * hd)
+    mask = None
+    if use_mask:
+        mask = (torch.rand(B, N, N) > 0.3)
+        idx = torch.arange(N)
+        mask[:, idx, idx] = True
+    qkv_d = qkv.to(dtype)           # quantise once so that both sides see the same inputs
+    dout_d = dout.to(dtype)
+    # oracle in fp64 on the CPU
+    q64 = qkv_d.double().requires_grad_(True)
+    q, k, v = [q64[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    o_ref, lse_ref = oracle.mhla_attn_core_closed_form(q, k, v, W, mask.double() if use_mask else None)
+    o_ref = o_ref.permute(0, 2, 1, 3).reshape(B, N, H * hd)
+    (o_ref * dout_d.double()).sum().backward()
+    # CUDA path
+    qc = qkv_d.cuda().requires_grad_(True)
+    mc = mask.to(torch.uint8).cuda() if use_mask else None
+    out, lse = ops.mhla_attn(qc, W, mc)
+    out.backward(dout_d.cuda())
+    assert out.dtype == dtype and lse.dtype == torch.float32
+    assert_close(out, o_ref, dtype, "out")
+    assert_close(lse, lse_ref, torch.float32 if dtype == torch.float32 else dtype, "lse")
+    assert_close(qc.grad, q64.grad, dtype, "dqkv")
+    for i, nm in enumerate("qkv"):
+        assert_close(qc.grad[:, :, i], q64.grad[:, :, i], dtype, "d" + nm, factor=2.0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B{}H{}N{}hd{}W{}{}".format(*c[:5], "m" if c[5] else ""))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_attn_core_matches_oracle(case, dtype):
+    _run(*case, dtype)
+
+
+def test_even_window_is_rejected_like_the_reference():
+    from favit_b200 import ops
+    qkv = torch.randn(1, 6, 3, 1, 64, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.mhla_attn(qkv, 4, None)
+
+
+def test_fully_masked_row_is_nan_like_softmax():
+    from favit_b200 import ops
+    qkv = torch.randn(1, 8, 3, 1, 64, device="cuda")
+    mask = torch.ones(1, 8, 8, dtype=torch.uint8, device="cuda")
+    mask[0, 3, :] = 0
+    out, _ = ops.mhla_attn(qkv, 3, mask)
+    assert torch.isnan(out[0, 3]).all()
+    assert torch.isfinite(out[0, :3]).all() and torch.isfinite(out[0, 4:]).all()
+
+
+def test_large_shape_properties():
+    """Full-size C4 slab: softmax rows are convex combinations -> |out| <= max |v| per head-dim; and the result does
+    not depend on how the batch is split (images are independent)."""
+    from favit_b200 import ops
+    torch.manual_seed(1)
+    B, N, H, hd, W = 64, 197, 12, 64, 7
+    qkv = torch.randn(B, N, 3, H, hd, device="cuda", dtype=torch.bfloat16)
+    out, lse = ops.mhla_attn(qkv, W, None)
+    vmax = qkv[:, :, 2].float().abs().amax(dim=1, keepdim=True).reshape(B, 1, H * hd)
+    assert (out.float().abs() <= vmax * 1.01 + 1e-3).all()
+    out2, _ = ops.mhla_attn(qkv[5:9].contiguous(), W, None)
+    assert torch.equal(out2, out[5:9])

@@ -1,0 +1,111 @@
+"""GPU parity: favit SPPP assignment (bit-exact integers) and segment-mean pooling against the golden fixtures produced
+by the reference and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _assign(lm, ps, img, r_cap=None):
+    from favit_b200.sppp import PatchToSuperpixelMapper
+    return PatchToSuperpixelMapper(ps).assign_batch(torch.from_numpy(lm).cuda(), img, r_cap)
+
+
+def test_assign_and_pool_match_reference_fixtures():
+    from favit_b200.sppp import PatchToSuperpixelMapper, SuperpixelPooling
+    g = golden("sppp_maps")
+    for name in [str(c) for c in g["cases"]]:
+        lm = g[f"{name}_map"]
+        ps, img = [int(v) for v in g[f"{name}_cfg"]]
+        emb = torch.from_numpy(g[f"{name}_emb"]).cuda()
+        a = _assign(lm, ps, img)
+        dicts = a.to_dicts()
+        mapper, pool = PatchToSuperpixelMapper(ps), SuperpixelPooling("mean")
+        for b in range(lm.shape[0]):
+            keys, lens, flat = g[f"{name}_{b}_keys"], g[f"{name}_{b}_lens"], g[f"{name}_{b}_flat"]
+            d = dicts[b]
+            assert list(d.keys()) == keys.tolist(), name
+            assert [len(v) for v in d.values()] == lens.tolist(), name
+            assert [p for v in d.values() for p in v] == flat.tolist(), name
+            R = len(keys)
+            assert int(a.num_slots[b]) == R
+            assert a.counts[b, :R].cpu().numpy().tolist() == lens.tolist()
+            # reference-signature path: map_patches on one image, pool with the dict it returned
+            d1 = mapper.map_patches(torch.from_numpy(lm[b]).cuda(), img)
+            assert list(d1.items()) == list(d.items())
+            pooled = pool.pool(emb[b], d1)
+            assert pooled.dtype == torch.float32 and pooled.shape == (R, emb.shape[-1])
+            assert torch.allclose(pooled.cpu(), torch.from_numpy(g[f"{name}_{b}_pooled"]), rtol=0, atol=2e-6), name
+            # a plain dict (not produced by map_patches) goes through the host-built CSR
+            pooled2 = pool.pool(emb[b], dict(d))
+            assert torch.equal(pooled2, pooled)
+
+
+@pytest.mark.parametrize("S,ps,K,B", [(32, 4, 4, 5), (224, 16, 16, 8), (224, 4, 16, 2), (512, 8, 64, 2), (96, 32, 9, 3)])
+def test_assign_bit_exact_vs_oracle(S, ps, K, B):
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(B, S, K, seed=S + ps, device="cpu").numpy()
+    ref = oracle.assign_oracle(lm, ps, S)
+    a = _assign(lm, ps, S)
+    assert np.array_equal(a.dom.cpu().numpy(), ref["dom"])
+    assert np.array_equal(a.slot.cpu().numpy(), ref["slot"])
+    assert np.array_equal(a.num_slots.cpu().numpy(), ref["num_slots"])
+    for b in range(B):
+        R = int(ref["num_slots"][b])
+        assert np.array_equal(a.counts[b, :R].cpu().numpy(), ref["counts"][b])
+        assert np.array_equal(a.slot_label[b, :R].cpu().numpy(), ref["slot_label"][b])
+        assert np.array_equal(a.offsets[b, :R + 1].cpu().numpy(), ref["offsets"][b])
+        assert np.array_equal(a.order[b].cpu().numpy(), ref["order"][b])
+
+
+def test_assign_adversarial_maps():
+    rng = np.random.default_rng(3)
+    # random labels per pixel from a small alphabet: many ties, negative and huge ids
+    alphabet = np.asarray([-7, 0, 3, 2 ** 40, 11, 5], dtype=np.int64)
+    lm = alphabet[rng.integers(0, len(alphabet), size=(4, 24, 24))]
+    ref = oracle.assign_oracle(lm, 4, 24)
+    a = _assign(lm, 4, 24)
+    assert np.array_equal(a.dom.cpu().numpy(), ref["dom"])
+    assert np.array_equal(a.slot.cpu().numpy(), ref["slot"])
+    assert np.array_equal(a.num_slots.cpu().numpy(), ref["num_slots"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B,S,ps,K,D", [(4, 32, 4, 4, 24), (8, 224, 16, 16, 384), (2, 128, 8, 16, 100)])
+def test_pool_fwd_bwd_vs_oracle(B, S, ps, K, D, dtype):
+    from favit_b200 import ops
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(B, S, K, seed=11, device="cpu", exact_k=True, patch_size=ps)
+    a = _assign(lm.numpy(), ps, S, r_cap=K)
+    P = (S // ps) ** 2
+    torch.manual_seed(0)
+    x = torch.randn(B, P, D).to(dtype)
+    g = torch.randn(B, K, D)
+    slot = a.slot.cpu().numpy()
+    ref = oracle.pool_mean_batched_oracle(x.float(), slot, K)
+    xc = x.cuda().requires_grad_(True)
+    out = ops.sppp_pool(xc, a.slot, a.counts, a.order, a.offsets, a.num_slots, K)
+    assert out.dtype == torch.float32
+    assert rel_err(out, ref) < 2e-6
+    out.backward(g.cuda())
+    cnt = torch.from_numpy(np.stack([np.bincount(slot[b], minlength=K) for b in range(B)])).double()
+    s64 = torch.from_numpy(slot.astype(np.int64))
+    dx_ref = torch.gather(g.double() / cnt[:, :, None], 1, s64[:, :, None].expand(-1, -1, D))
+    assert xc.grad.dtype == dtype
+    assert rel_err(xc.grad, dx_ref) < (1e-6 if dtype == torch.float32 else 8e-3)
+
+
+def test_unequal_slot_counts_raise():
+    from favit_b200.sppp import PatchToSuperpixelMapper, SuperpixelPooling
+    lm = torch.zeros(2, 16, 16, dtype=torch.int64)
+    lm[1, :, 8:] = 1                      # image 0 has one superpixel, image 1 has two
+    a = PatchToSuperpixelMapper(4).assign_batch(lm.cuda(), 16)
+    x = torch.randn(2, 16, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        SuperpixelPooling("mean").pool_batch(x, a, 2)
+    with pytest.raises(ValueError):
+        SuperpixelPooling("median").pool(x[0], {0: [0]})
