@@ -22,6 +22,12 @@ from .mhla_oracle import (  # noqa: F401
     mhla_attn_core_closed_form,
     fold_latent,
 )
+from .models_oracle import (  # noqa: F401
+    vit_mhla_forward,
+    sppp_vit_mhla_forward,
+    superpixel_centroids,
+    dynamic_positional_encoding,
+)
 from .sppp_oracle import (  # noqa: F401
     map_patches_oracle,
     assign_oracle,

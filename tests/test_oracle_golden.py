@@ -100,3 +100,40 @@ def test_sppp_assign_and_pool_match_reference():
             assert torch.allclose(pooled, torch.from_numpy(g[f"{name}_{b}_pooled"]), rtol=0, atol=1e-6)
             batched = oracle.pool_mean_batched_oracle(emb[b:b + 1], res["slot"][b:b + 1], len(keys))
             assert torch.allclose(batched[0].float(), pooled, atol=1e-6)
+
+
+def _model_sd(g, prefix, dtype):
+    sd = {}
+    for k in g.files:
+        if k.startswith(prefix + "_sd_"):
+            sd[k[len(prefix) + 4:]] = torch.from_numpy(g[k]).to(dtype).requires_grad_(True)
+    return sd
+
+
+def test_vit_mhla_model_matches_reference_fp64():
+    g = _load("models")
+    sd = _model_sd(g, "vit", torch.float64)
+    y = oracle.vit_mhla_forward(torch.from_numpy(g["vit_x"]), sd, patch_size=4, num_heads=2, window=3)
+    assert torch.allclose(y, torch.from_numpy(g["vit_y"]), rtol=1e-9, atol=1e-11)
+    loss = torch.nn.functional.cross_entropy(y, torch.from_numpy(g["vit_labels"]))
+    assert abs(loss.item() - float(g["vit_loss"])) < 1e-10
+    loss.backward()
+    for k, p in sd.items():
+        ref = torch.from_numpy(g[f"vit_grad_{k}"])
+        assert torch.allclose(p.grad, ref, rtol=1e-8, atol=1e-11), k
+
+
+def test_sppp_vit_mhla_model_matches_reference_fp32():
+    g = _load("models")
+    sd = _model_sd(g, "sppp", torch.float32)
+    seg = torch.from_numpy(g["sppp_maps"])
+    y = oracle.sppp_vit_mhla_forward(torch.from_numpy(g["sppp_x"]), seg, sd, patch_size=8, num_heads=2, window=3,
+                                     num_superpixels=4)
+    assert torch.allclose(y, torch.from_numpy(g["sppp_y"]), rtol=1e-4, atol=1e-5)
+    loss = torch.nn.functional.cross_entropy(y, torch.from_numpy(g["sppp_labels"]))
+    assert abs(loss.item() - float(g["sppp_loss"])) < 1e-5
+    loss.backward()
+    for k, p in sd.items():
+        ref = torch.from_numpy(g[f"sppp_grad_{k}"])
+        scale = max(ref.abs().max().item(), 1e-6)
+        assert (p.grad - ref).abs().max().item() <= 2e-4 * scale + 1e-7, k
