@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the favit_b200 hot path: images/sec, fwd+bwd, ViT-MHLA 224px on N x B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl favit|reference]
+
+N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...` (one rank per GPU,
+NCCL).  Rank 0 prints ONE JSON line.  A step = zero_grad -> forward (bf16 autocast) -> cross-entropy -> backward with
+the bucketed gradient all-reduce overlapped -> AdamW step, on a fixed per-GPU batch of synthetic images (weak scaling).
+
+Workloads:
+  vitb16_mhla_224    VisionTransformerMHLA ViT-B/16, 224px, window 7, per-GPU batch 256       (BASELINE configs[3]; default)
+  sppp_vits_mhla_224 SPPPViTMHLA ViT-S/16, 224px, 16 superpixels, window 7, per-GPU batch 256  (BASELINE configs[1])
+
+`--impl reference` times the CPU restatement of the reference (oracle/, the reference itself is Python and does not
+travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "vitb16_mhla_224": dict(kind="vit", img=224, ps=16, D=768, depth=12, H=12, W=7, classes=1000, B=256, cpu_B=8),
+    "sppp_vits_mhla_224": dict(kind="sppp", img=224, ps=16, D=384, depth=12, H=6, W=7, K=16, classes=1000, B=256,
+                               cpu_B=16),
+}
+METRIC = "images/sec fwd+bwd ViT-MHLA 224px"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+def build_model(wl, device):
+    import favit_b200  # noqa: F401
+    from favit_b200.models import SPPPViTMHLA, VisionTransformerMHLA
+    torch.manual_seed(1234)
+    if wl["kind"] == "vit":
+        m = VisionTransformerMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
+                                  depth=wl["depth"], num_heads=wl["H"], window_size=wl["W"], use_mhla=True)
+    else:
+        m = SPPPViTMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
+                        depth=wl["depth"], num_heads=wl["H"], num_superpixels=wl["K"], window_size=wl["W"],
+                        use_mhla=True, pooling_type="mean")
+    return m.to(device)
+
+
+def make_batch(wl, B, seed, device):
+    from favit_b200 import synth
+    x = synth.images(B, wl["img"], seed=seed, device=device)
+    y = synth.class_labels(B, wl["classes"], seed=seed, device=device)
+    maps = None
+    if wl["kind"] == "sppp":
+        maps = synth.voronoi_label_maps(B, wl["img"], wl["K"], seed=seed, device=device, exact_k=True,
+                                        patch_size=wl["ps"])
+    return x, y, maps
+
+
+class ClockSampler:
+    """SM clock and throttle reasons during the timed region (pynvml; B200_PROFILING.md 'clocks line')."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        if not self.samples:
+            return None
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(wl, B):
+    """Returns (step, n_images): one fwd + CE + bwd + AdamW step of the oracle model on B images (fp32, CPU)."""
+    import oracle
+    from favit_b200.models import SPPPViTMHLA, VisionTransformerMHLA  # constructors only (parameter shapes / init)
+    torch.manual_seed(1234)
+    if wl["kind"] == "vit":
+        m = VisionTransformerMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
+                                  depth=wl["depth"], num_heads=wl["H"], window_size=wl["W"], use_mhla=True)
+    else:
+        m = SPPPViTMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
+                        depth=wl["depth"], num_heads=wl["H"], num_superpixels=wl["K"], window_size=wl["W"],
+                        use_mhla=True)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    del m
+    opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, weight_decay=0.05)
+    x, y, maps = make_batch(wl, B, seed=1234, device="cpu")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        if wl["kind"] == "vit":
+            logits = oracle.vit_mhla_forward(x, sd, wl["ps"], wl["H"], wl["W"])
+        else:
+            logits = oracle.sppp_vit_mhla_forward(x, maps, sd, wl["ps"], wl["H"], wl["W"], wl["K"])
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step, B
+
+
+def time_cpu_oracle(wl, B, warmup, steps):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, n = cpu_oracle_step_fn(wl, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt * 1e3, cores
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    B = wl["cpu_B"]
+    ips, ms, cores = time_cpu_oracle(wl, B, args.warmup, args.steps)
+    sample = f"{B} images/step of {args.workload}, fp32, oracle port of the reference modules, AdamW step included"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_step": B, "device": "cpu"},
+        "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# favit arm
+# --------------------------------------------------------------------------------------------------
+def timed_steps(fn, steps, dist_on, device):
+    """K steps bracketed by barrier + synchronize, timed with CUDA events; returns the max over ranks (ms total)."""
+    import torch.distributed as dist
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if dist_on:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_favit(args, wl, rank, world, local_rank):
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=favit) needs a B200: the favit kernels have no CPU fallback")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=device)
+    import favit_b200
+    from favit_b200 import _lib as L
+    from favit_b200.engine import HostBatchFeeder, TrainStep
+    cc = L.lib().favit_device_cc()
+    if cc != 100:
+        raise RuntimeError(f"favit_b200 is built for sm_100a only; this device reports compute capability {cc}")
+
+    B = args.batch or wl["B"]
+    model = build_model(wl, device)
+    if wl["kind"] == "sppp":
+        model.validate_slots = False          # synthetic maps are validated once, below, not once per step
+    step = TrainStep(model, process_group=None)
+    # distinct batches so that no step can reuse a cached input; seed differs per rank
+    nb = 2
+    batches = [make_batch(wl, B, seed=1234 + rank * 100 + i, device=device) for i in range(nb)]
+    if wl["kind"] == "sppp":
+        for (_, _, maps) in batches:
+            a = model.patch_mapper.assign_batch(maps, wl["img"], r_cap=wl["K"])
+            assert int(a.num_slots.min()) == wl["K"] == int(a.num_slots.max()), "synthetic label maps must give R == K"
+
+    def dev_step(i):
+        x, y, maps = batches[i % nb]
+        return step(x, y, maps)
+
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize(device)
+
+    # ---- device-resident throughput (`value`) with per-launch event timing for the roofline ----
+    sampler = ClockSampler(local_rank)
+    L.PROFILE = []
+    launches0 = L.launch_count()
+    sampler.start()
+    ms_total = timed_steps(dev_step, args.steps, dist_on, device)
+    clocks = sampler.stop()
+    launches = L.launch_count() - launches0
+    prof, L.PROFILE = L.PROFILE, None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    fam = {}
+    for name, work, e0, e1 in prof:
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        f[0] += work
+        f[1] += e0.elapsed_time(e1)
+        f[2] += 1
+    peaks = load_peaks()
+    gemm = [fam[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in fam]
+    g_work, g_ms, g_n = (sum(v[0] for v in gemm), sum(v[1] for v in gemm), sum(v[2] for v in gemm)) if gemm else (0, 1, 0)
+    achieved = g_work / (g_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "gemm_bf16_tcgen05_kernel (MHLA qkv/proj fwd+dgrad+wgrad launches of the timed region)",
+        "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+        "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+        "launches": g_n, "share_of_step": round(g_ms / ms_total, 4),
+    }
+    families = {k: {"launches": v[2], "ms_per_step": round(v[1] / args.steps, 4),
+                    ("gbps" if k.startswith(("sppp", "attn")) else "tflops"):
+                        round(v[0] / (v[1] * 1e-3) / (1e9 if k.startswith(("sppp", "attn")) else 1e12), 2)}
+                for k, v in fam.items() if v[1] > 0}
+    for k, v in families.items():
+        if "gbps" in v:
+            v["frac_hbm"] = round(v["gbps"] / peaks["hbm"], 4)
+
+    # ---- end to end from pinned host memory (`e2e`) ----
+    host = [tuple(None if t is None else t.cpu().pin_memory() for t in b) for b in batches]
+    h2d = sum(t.numel() * t.element_size() for t in host[0] if t is not None)
+    feeder = HostBatchFeeder(device, 3)
+    loss_host = torch.zeros(1, pin_memory=True)
+
+    def e2e_step(i):
+        if i == 0:
+            feeder.prefetch(host[0])
+        x, y, maps = feeder.get(i)
+        if i + 1 < args.steps:
+            feeder.prefetch(host[(i + 1) % nb])      # H2D of step i+1 overlaps step i
+        loss = step(x, y, maps)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the loss is read on the host every step (reference: loss.item())
+        return float(loss_host[0])
+
+    feeder.i = 0
+    e2e_ms = timed_steps(e2e_step, args.steps, dist_on, device) / args.steps
+    e2e_value = world * B / (e2e_ms / 1e3)
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "global_batch": world * B, "per_gpu_batch": B, "img": wl["img"],
+                   "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"], "window": wl["W"],
+                   "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "adamw(fused) in step",
+                   "l2": "working set >> L2 every step (inputs %.0f MB, activations several GB); no flush needed"
+                         % (h2d / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 3),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernel_families": families,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = time_cpu_oracle(wl, wl["cpu_B"], 1, 2)
+        out["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+                               "sample": f"{wl['cpu_B']} images/step of {args.workload} (fp32 oracle port, 1 warm-up + 2 "
+                                         f"timed steps, AdamW included)"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="favit", choices=["favit", "reference"])
+    ap.add_argument("--workload", default="vitb16_mhla_224", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "favit":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run "
+                         f"--nproc-per-node {args.gpus}")
+    run_favit(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

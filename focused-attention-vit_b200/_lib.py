@@ -66,3 +66,24 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().favit_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py's roofline): when `PROFILE` is a list, every C call is bracketed by CUDA
+# events on the current torch stream and (family, algorithmic work, start, end) is appended to it.
+# ------------------------------------------------------------------------------------------------
+PROFILE = None
+
+
+def call(family: str, work: float, fn, *args) -> int:
+    """Invoke a C-ABI function; `work` = algorithmic FLOPs (GEMM/attention) or bytes (SPPP) of this launch."""
+    if PROFILE is None:
+        return fn(*args)
+    import torch
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    PROFILE.append((family, work, e0, e1))
+    return rc

@@ -1,0 +1,106 @@
+"""Data-parallel gradient all-reduce overlapped with backward (one process per GPU, NCCL over NVLink 5 / NVSwitch).
+
+The reference is single-process (no DDP); this is new work.  Parameters are packed, in reverse
+registration order (the order backward produces their gradients), into flat fp32 buckets; every `param.grad` is a view
+into its bucket, so there is no gather copy.  A post-accumulate-grad hook counts a bucket's gradients down and, when the
+bucket is complete, launches an asynchronous all-reduce(AVG) on it: NCCL runs on its own stream, ordered after the
+backward kernels that produced the bucket, while the rest of backward keeps running on the compute stream.
+`finish()` makes the compute stream wait for the outstanding reductions before the optimizer reads the gradients.
+
+Every op on the path is per image (no BatchNorm, no cross-sample statistic), so averaged gradients of B/N-image shards
+equal the gradient of the B-image batch with a mean loss.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradAllReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 32.0, process_group=None,
+                 enabled: Optional[bool] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = process_group
+        if enabled is None:
+            enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.enabled = enabled
+        self.world = dist.get_world_size(process_group) if self.enabled else 1
+        cap = int(bucket_mb * (1 << 20)) // 4
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._size = []
+        cur: List[torch.nn.Parameter] = []
+        n = 0
+        groups = []
+        for p in reversed(self.params):
+            if cur and n + p.numel() > cap:
+                groups.append(cur)
+                cur, n = [], 0
+            cur.append(p)
+            n += p.numel()
+        if cur:
+            groups.append(cur)
+        for bi, g in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in g), dtype=torch.float32, device=g[0].device)
+            off = 0
+            for p in g:
+                if p.dtype != torch.float32:
+                    raise TypeError("GradAllReducer expects fp32 master parameters")
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[p] = bi
+            self.buckets.append(flat)
+            self._size.append(len(g))
+        self._pending = list(self._size)
+        self._works = []
+        self._handles = []
+        if self.enabled:
+            # gloo has no AVG: sum and scale afterwards
+            self._avg = dist.ReduceOp.AVG if dist.get_backend(process_group) == "nccl" else None
+            for p in self.params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    # -- per step ---------------------------------------------------------------------------------
+    def zero_grad(self) -> None:
+        for b in self.buckets:
+            b.zero_()
+        self._pending = list(self._size)
+        self._works = []
+
+    def _hook(self, p: torch.nn.Parameter) -> None:
+        bi = self._bucket_of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            flat = self.buckets[bi]
+            if self._avg is not None:
+                w = dist.all_reduce(flat, op=self._avg, group=self.group, async_op=True)
+            else:
+                w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append((w, bi))
+
+    def finish(self) -> None:
+        """Wait (stream-wise on CUDA) for every outstanding bucket; reduce buckets whose hooks did not all fire
+        (parameters unused in this step keep a zero gradient)."""
+        if not self.enabled:
+            return
+        for bi, left in enumerate(self._pending):
+            if left != 0:
+                op = self._avg if self._avg is not None else dist.ReduceOp.SUM
+                self._works.append((dist.all_reduce(self.buckets[bi], op=op, group=self.group, async_op=True), bi))
+                self._pending[bi] = 0
+        for w, bi in self._works:
+            w.wait()
+            if self._avg is None:
+                self.buckets[bi].div_(self.world)
+        self._works = []
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    @property
+    def grad_bytes(self) -> int:
+        return sum(b.numel() * 4 for b in self.buckets)

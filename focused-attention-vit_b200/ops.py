@@ -76,7 +76,7 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[
         residual = _rowmajor(residual)
     if M == 0:
         return y, pre
-    rc = L.lib().favit_linear_fwd(
+    rc = L.call("gemm_fwd", 2.0 * M * N * K, L.lib().favit_linear_fwd,
         _p(x), _p(w), _p(bias), _p(residual), _p(y), _p(pre) if pre.numel() else None, M, N, K, _ld(x), _ld(w), N,
         _ld(residual) if residual is not None else 0, _dt(x), _DT[out_dtype],
         _dt(residual) if residual is not None else L.F32, L.EPI_GELU if gelu else L.EPI_NONE, _stream())
@@ -105,7 +105,7 @@ def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: tor
         preact = preact.contiguous()
     if M == 0:
         return dx
-    rc = L.lib().favit_linear_dgrad(_p(dy), _p(w), _p(preact), _p(dx), M, N, K, _ld(dy), _ld(w), K, _dt(dy),
+    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), M, N, K, _ld(dy), _ld(w), K, _dt(dy),
                                     _DT[out_dtype], L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _stream())
     L.check(rc, "favit_linear_dgrad")
     return dx
@@ -129,7 +129,7 @@ def linear_wgrad(dy: Tensor, x: Tensor, want_bias: bool) -> Tuple[Tensor, Tensor
     db = torch.empty((N,) if want_bias else (0,), dtype=torch.float32, device=dy.device)
     if M == 0:
         return dw.zero_(), db.zero_()
-    rc = L.lib().favit_linear_wgrad(_p(dy), _p(x), _p(dw), _p(db) if want_bias else None, M, N, K, _ld(dy), _ld(x), K,
+    rc = L.call("gemm_wgrad", 2.0 * M * N * K, L.lib().favit_linear_wgrad, _p(dy), _p(x), _p(dw), _p(db) if want_bias else None, M, N, K, _ld(dy), _ld(x), K,
                                     _dt(dy), 0, _stream())
     L.check(rc, "favit_linear_wgrad")
     return dw, db
@@ -209,7 +209,7 @@ def mhla_attn_fwd(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Ten
         raise ValueError("mhla_attn: mask must be a contiguous uint8 [B,N,N] tensor")
     if B * N == 0:
         return out, lse
-    rc = L.lib().favit_mhla_attn_fwd(q, k, v, _p(mask), _p(out), _p(lse), B, H, N, hd, window, float(hd) ** -0.5,
+    rc = L.call("attn_fwd", 4.0 * B * N * H * hd * qkv.element_size(), L.lib().favit_mhla_attn_fwd, q, k, v, _p(mask), _p(out), _p(lse), B, H, N, hd, window, float(hd) ** -0.5,
                                      sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
     L.check(rc, "favit_mhla_attn_fwd")
     return out, lse
@@ -235,7 +235,7 @@ def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: i
         return dqkv
     es = qkv.element_size()
     dq = dqkv.data_ptr()
-    rc = L.lib().favit_mhla_attn_bwd(q, k, v, _p(mask), _p(out), _p(lse), _p(dout), dq, dq + H * hd * es,
+    rc = L.call("attn_bwd", 8.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_bwd, q, k, v, _p(mask), _p(out), _p(lse), _p(dout), dq, dq + H * hd * es,
                                      dq + 2 * H * hd * es, _p(delta), B, H, N, hd, window, float(hd) ** -0.5,
                                      sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
     L.check(rc, "favit_mhla_attn_bwd")
@@ -303,7 +303,8 @@ def sppp_assign(labels: Tensor, patch_size: int, img_size: int, r_cap: int) -> L
     offsets = torch.empty((B, r_cap + 1), dtype=torch.int32, device=dev)
     order = torch.empty((B, P), dtype=torch.int32, device=dev)
     if B * P:
-        rc = L.lib().favit_sppp_assign(_p(labels), B, Hh, Ww, patch_size, g, _p(dom), _p(slot), _p(num_slots),
+        work = B * Hh * Ww * 8.0 + 2.0 * B * P * 4 + B * r_cap * 4
+        rc = L.call("sppp_assign", work, L.lib().favit_sppp_assign, _p(labels), B, Hh, Ww, patch_size, g, _p(dom), _p(slot), _p(num_slots),
                                        _p(counts), _p(slot_label), _p(offsets), _p(order), r_cap, _stream())
         L.check(rc, "favit_sppp_assign")
     return [dom, slot, num_slots, counts, slot_label, offsets, order]
@@ -329,7 +330,8 @@ def sppp_pool_fwd(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, 
     r_cap = offsets.shape[1] - 1
     out = torch.empty((B, R, D), dtype=out_dtype, device=x.device)
     if out.numel():
-        rc = L.lib().favit_sppp_pool_fwd(_p(x), _dt(x), _p(order), _p(offsets), _p(num_slots), _p(out), _DT[out_dtype],
+        work = float(x.numel() * x.element_size() + B * P * 4 + out.numel() * out.element_size() + B * R * 4)
+        rc = L.call("sppp_pool_fwd", work, L.lib().favit_sppp_pool_fwd, _p(x), _dt(x), _p(order), _p(offsets), _p(num_slots), _p(out), _DT[out_dtype],
                                          B, P, R, D, r_cap, _stream())
         L.check(rc, "favit_sppp_pool_fwd")
     return out
@@ -349,7 +351,8 @@ def sppp_pool_bwd(dout: Tensor, slot: Tensor, counts: Tensor, dx_dtype: torch.dt
     r_cap = counts.shape[1]
     dx = torch.empty((B, P, D), dtype=dx_dtype, device=dout.device)
     if dx.numel():
-        rc = L.lib().favit_sppp_pool_bwd(_p(dout), _dt(dout), _p(slot), _p(counts), _p(dx), _DT[dx_dtype], B, P, R, D,
+        work = float(dout.numel() * dout.element_size() + B * P * 4 + dx.numel() * dx.element_size())
+        rc = L.call("sppp_pool_bwd", work, L.lib().favit_sppp_pool_bwd, _p(dout), _dt(dout), _p(slot), _p(counts), _p(dx), _DT[dx_dtype], B, P, R, D,
                                          r_cap, _stream())
         L.check(rc, "favit_sppp_pool_bwd")
     return dx
