@@ -1,0 +1,273 @@
+// LayerNorm forward / backward for the transformer block around MHLA (sm_100a).
+//
+// "Next" row of SURVEY.md §8f: the block wrapper /root/reference/models/vit_mhla.py:77-109 (norm1 -> attn -> residual,
+// norm2 -> mlp -> residual) runs nn.LayerNorm in fp32 under autocast and hands bf16 to the linears.  These kernels keep
+// that numerics (fp32 statistics, two-pass variance) and fuse what surrounds the norm:
+//   forward : y = (x - mean) * rstd * gamma + beta, written directly in the GEMM's operand dtype (bf16), mean/rstd saved
+//   backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//             + the residual-stream gradient that bypasses the norm (dres), written as fp32 and, optionally, a bf16 copy
+//             that the next dgrad / wgrad GEMM reads as its operand; dgamma / dbeta are accumulated per column.
+// HBM-bound byte movers: one warp per row, 16-byte vector loads, the row stays in registers between the passes.
+#include "favit_common.cuh"
+
+namespace favit {
+namespace {
+
+constexpr int kMaxVec = 8;  // float4 per lane: rows up to 32 * 4 * 8 = 1024 elements live in registers
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&f)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&f)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&f)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// D % 4 == 0, D <= 1024.  Lane l owns float4 chunks l, l+32, ... (coalesced 512-byte warp accesses).
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, TY* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int D,
+                                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = D >> 2;
+  const TX* xr = x + (int64_t)row * D;
+  float v[NV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      load4(xr + 4 * c, v[i]);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+  }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = v[i][e] - mu;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)D + eps);
+  TY* yr = y + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float g[4], b[4], o[4];
+      load4(gamma + 4 * c, g);
+      load4(beta + 4 * c, b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mu) * rs, g[e], b[e]);
+      store4(yr + 4 * c, o);
+    }
+  }
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+
+// Persistent over rows: warp w handles rows w, w + total_warps, ...; per-lane dgamma/dbeta partials stay in registers
+// and are combined through shared memory, then one atomic per column per CTA.
+template <typename TX, typename TDY, int NV>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                                                     int D) {
+  extern __shared__ float s_red[];  // [2][warps][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nvec = D >> 2;
+  float dg[NV][4], db[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
+  const float invD = 1.f / (float)D;
+  for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
+    const TX* xr = x + (int64_t)row * D;
+    const TDY* dyr = dy + (int64_t)row * D;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][4], gy[NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float xv[4], dv[4], g[4];
+        load4(xr + 4 * c, xv);
+        load4(dyr + 4 * c, dv);
+        load4(gamma + 4 * c, g);  // L1-resident
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xh[i][e] = (xv[e] - mu) * rs;
+          gy[i][e] = dv[e] * g[e];
+          s1 += gy[i][e];
+          s2 = fmaf(gy[i][e], xh[i][e], s2);
+          dg[i][e] = fmaf(dv[e], xh[i][e], dg[i][e]);
+          db[i][e] += dv[e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
+        if (dres) {
+          float r[4];
+          load4(dres + (int64_t)row * D + 4 * c, r);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] += r[e];
+        }
+        store4(dx + (int64_t)row * D + 4 * c, o);
+        if (dx_bf16) store4(dx_bf16 + (int64_t)row * D + 4 * c, o);
+      }
+    }
+  }
+  if (dgamma == nullptr) return;
+  float* sg = s_red;
+  float* sb = s_red + (size_t)nwarps * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sg[warp * D + 4 * c + e] = dg[i][e];
+        sb[warp * D + 4 * c + e] = db[i][e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      a += sg[w * D + c];
+      b += sb[w * D + c];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+}  // namespace
+}  // namespace favit
+
+using namespace favit;
+
+extern "C" int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const float* gamma, const float* beta, void* y,
+                                   favit_dtype y_dtype, float* mean, float* rstd, int M, int D, float eps,
+                                   favit_stream stream) {
+  FAVIT_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  FAVIT_CHECK_ARG(M > 0 && D > 0, "layernorm_fwd: M, D must be positive");
+  if (D % 4 != 0 || D > 128 * kMaxVec) {
+    set_error("layernorm_fwd: D=%d unsupported (needs D %% 4 == 0 and D <= %d)", D, 128 * kMaxVec);
+    return FAVIT_ERR_UNSUPPORTED;
+  }
+  FAVIT_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)gamma % 16 == 0) &&
+                      ((uintptr_t)beta % 16 == 0),
+                  "layernorm_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)ceil_div(M, 8);
+#define LN_FWD_NV(TX, TY, NV) \
+  ln_fwd_kernel<TX, TY, NV><<<blocks, 256, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, M, D, eps)
+#define LN_FWD(TX, TY)                            \
+  do {                                            \
+    if (D <= 256) LN_FWD_NV(TX, TY, 2);           \
+    else if (D <= 512) LN_FWD_NV(TX, TY, 4);      \
+    else if (D <= 768) LN_FWD_NV(TX, TY, 6);      \
+    else LN_FWD_NV(TX, TY, 8);                    \
+  } while (0)
+  if (x_dtype == FAVIT_F32 && y_dtype == FAVIT_BF16) LN_FWD(float, __nv_bfloat16);
+  else if (x_dtype == FAVIT_F32 && y_dtype == FAVIT_F32) LN_FWD(float, float);
+  else if (x_dtype == FAVIT_BF16 && y_dtype == FAVIT_BF16) LN_FWD(__nv_bfloat16, __nv_bfloat16);
+  else if (x_dtype == FAVIT_BF16 && y_dtype == FAVIT_F32) LN_FWD(__nv_bfloat16, float);
+  else {
+    set_error("layernorm_fwd: bad dtype");
+    return FAVIT_ERR_ARG;
+  }
+#undef LN_FWD
+#undef LN_FWD_NV
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+extern "C" int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const void* x, favit_dtype x_dtype,
+                                   const float* mean, const float* rstd, const float* gamma, const float* dres,
+                                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, int M, int D,
+                                   favit_stream stream) {
+  FAVIT_CHECK_ARG(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
+  FAVIT_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta come together");
+  FAVIT_CHECK_ARG(M > 0 && D > 0, "layernorm_bwd: M, D must be positive");
+  if (D % 4 != 0 || D > 128 * kMaxVec) {
+    set_error("layernorm_bwd: D=%d unsupported (needs D %% 4 == 0 and D <= %d)", D, 128 * kMaxVec);
+    return FAVIT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int warps = 4;
+  const size_t smem = (size_t)2 * warps * D * sizeof(float);  // <= 32 KiB
+  const unsigned blocks = (unsigned)max(1, min(ceil_div(M, warps), 8 * num_sms()));
+#define LN_BWD_NV(TX, TDY, NV)                                                                                   \
+  ln_bwd_kernel<TX, TDY, NV><<<blocks, warps * 32, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
+                                                               dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, D)
+#define LN_BWD(TX, TDY)                           \
+  do {                                            \
+    if (D <= 256) LN_BWD_NV(TX, TDY, 2);          \
+    else if (D <= 512) LN_BWD_NV(TX, TDY, 4);     \
+    else if (D <= 768) LN_BWD_NV(TX, TDY, 6);     \
+    else LN_BWD_NV(TX, TDY, 8);                   \
+  } while (0)
+  if (x_dtype == FAVIT_F32 && dy_dtype == FAVIT_BF16) LN_BWD(float, __nv_bfloat16);
+  else if (x_dtype == FAVIT_F32 && dy_dtype == FAVIT_F32) LN_BWD(float, float);
+  else if (x_dtype == FAVIT_BF16 && dy_dtype == FAVIT_BF16) LN_BWD(__nv_bfloat16, __nv_bfloat16);
+  else if (x_dtype == FAVIT_BF16 && dy_dtype == FAVIT_F32) LN_BWD(__nv_bfloat16, float);
+  else {
+    set_error("layernorm_bwd: bad dtype");
+    return FAVIT_ERR_ARG;
+  }
+#undef LN_BWD
+#undef LN_BWD_NV
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}

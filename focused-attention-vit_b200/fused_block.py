@@ -1,0 +1,160 @@
+"""The whole transformer block around MHLA as two torch.library ops (`favit::block_fwd`, `favit::block_bwd`) made only
+of favit kernels — the "next" row 1 of SURVEY.md §8f on top of the hot path.
+
+Replaces /root/reference/models/vit_mhla.py:77-109 (TransformerBlock.forward with use_mhla=True: norm1 -> MHLA ->
+residual -> norm2 -> MLP -> residual; MLP = models/vit.py:125-139) and its autograd, for the cases every model in the
+reference uses: no attention mask, dropout inactive.
+
+Dataflow (M = B*N tokens; cd = compute dtype, bf16 under autocast or fp32):
+  forward   x (fp32 residual stream) -LN1-> xn (cd) -GEMM+bias-> qkv (cd) -window attention-> o (cd)
+            -GEMM+bias+residual(x)-> x2 (fp32) -LN2-> xn2 (cd) -GEMM+bias+GELU-> h (cd; pre-activation saved)
+            -GEMM+bias+residual(x2)-> x3 (fp32)
+  backward  every dgrad / wgrad is the tcgen05 GEMM (MN-major operands, no transposes), GELU' is fused into the fc2
+            dgrad epilogue, the residual-gradient add and the bf16 operand copy are fused into the LayerNorm backward.
+The latent projection is folded into the qkv / proj weights by the caller (mhla.fold_latent, a few [hd x hd] torch
+matmuls whose autograd yields the latent_proj gradients).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import Tensor
+
+from . import raw
+
+# bf16 copy of the residual-stream gradient produced by a block's backward, handed to the next block's backward
+# (autograd only carries the fp32 gradient).  Keyed by the fp32 tensor's storage address; consumed once.
+_GRAD_BF16 = {}
+
+
+@torch.library.custom_op("favit::block_fwd", mutates_args=())
+def block_fwd(x: Tensor, ln1_w: Tensor, ln1_b: Tensor, wqkv: Tensor, bqkv: Tensor, wproj: Tensor, bproj: Tensor,
+              ln2_w: Tensor, ln2_b: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, B: int, N: int, H: int,
+              window: int, eps1: float, eps2: float) -> List[Tensor]:
+    """x [B*N, D] fp32; GEMM weights already in the compute dtype (bf16 or fp32), biases / LN parameters fp32.
+    Returns [x3, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h]."""
+    M, D = x.shape
+    cd = wqkv.dtype
+    hd = D // H
+    _GRAD_BF16.clear()      # entries of an earlier backward pass must never be matched by a recycled address
+    xn, mu1, rs1 = raw.ln_fwd(x, ln1_w, ln1_b, cd, eps1)
+    qkv, _ = raw.linear_fwd(xn, wqkv, bqkv, None, cd)
+    o, lse = raw.attn_fwd(qkv, B, N, H, hd, window)
+    x2, _ = raw.linear_fwd(o, wproj, bproj, x, torch.float32)
+    xn2, mu2, rs2 = raw.ln_fwd(x2, ln2_w, ln2_b, cd, eps2)
+    h, hpre = raw.linear_fwd(xn2, w1, b1, None, cd, gelu=True, save_preact=True)
+    x3, _ = raw.linear_fwd(h, w2, b2, x2, torch.float32)
+    return [x3, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h]
+
+
+@block_fwd.register_fake
+def _(x, ln1_w, ln1_b, wqkv, bqkv, wproj, bproj, ln2_w, ln2_b, w1, b1, w2, b2, B, N, H, window, eps1, eps2):
+    M, D = x.shape
+    cd = wqkv.dtype
+    f32 = torch.float32
+    e = lambda shape, dt: x.new_empty(shape, dtype=dt)
+    Hd = w1.shape[0]
+    return [e((M, D), f32), e((M, D), cd), e((M,), f32), e((M,), f32), e((M, 3 * D), cd), e((M, D), cd),
+            e((B, H, N), f32), e((M, D), f32), e((M, D), cd), e((M,), f32), e((M,), f32), e((M, Hd), cd),
+            e((M, Hd), cd)]
+
+
+@torch.library.custom_op("favit::block_bwd", mutates_args=())
+def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, ln2_w: Tensor, w1: Tensor, w2: Tensor,
+              xn: Tensor, mu1: Tensor, rs1: Tensor, qkv: Tensor, o: Tensor, lse: Tensor, x2: Tensor, xn2: Tensor,
+              mu2: Tensor, rs2: Tensor, hpre: Tensor, h: Tensor, B: int, N: int, H: int, window: int) -> List[Tensor]:
+    """Returns [dx, dln1_w, dln1_b, dwqkv, dbqkv, dwproj, dbproj, dln2_w, dln2_b, dw1, db1, dw2, db2] (all fp32)."""
+    M, D = x.shape
+    cd = wqkv.dtype
+    hd = D // H
+    bf = cd == torch.bfloat16
+    g = g.contiguous()
+    if bf:
+        g_c = _GRAD_BF16.pop((g.data_ptr(), M, D), None)
+        if g_c is None:
+            g_c = g.to(cd)
+    else:
+        g_c = g
+    dw2, db2 = raw.linear_wgrad(g_c, h)
+    dhpre = raw.linear_dgrad(g_c, w2, hpre, cd)
+    dw1, db1 = raw.linear_wgrad(dhpre, xn2)
+    dxn2 = raw.linear_dgrad(dhpre, w1, None, cd)
+    g2, g2_b, dg2, dbt2 = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf)
+    g2_c = g2_b if bf else g2
+    dwp, dbp = raw.linear_wgrad(g2_c, o)
+    do = raw.linear_dgrad(g2_c, wproj, None, cd)
+    dqkv = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window)
+    dwq, dbq = raw.linear_wgrad(dqkv, xn)
+    dxn = raw.linear_dgrad(dqkv, wqkv, None, cd)
+    g0, g0_b, dg1, dbt1 = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf)
+    if bf:
+        _GRAD_BF16.clear()                      # at most one hand-over is alive
+        _GRAD_BF16[(g0.data_ptr(), M, D)] = g0_b
+    return [g0, dg1, dbt1, dwq, dbq, dwp, dbp, dg2, dbt2, dw1, db1, dw2, db2]
+
+
+@block_bwd.register_fake
+def _(g, x, ln1_w, wqkv, wproj, ln2_w, w1, w2, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h, B, N, H, window):
+    f32 = torch.float32
+    e = lambda t: t.new_empty(t.shape, dtype=f32)
+    D = x.shape[1]
+    v = lambda n: x.new_empty((n,), dtype=f32)
+    return [e(x), v(D), v(D), e(wqkv), v(wqkv.shape[0]), e(wproj), v(D), v(D), v(D), e(w1), v(w1.shape[0]), e(w2), v(D)]
+
+
+class FusedBlockFn(torch.autograd.Function):
+    """x [B,N,D] fp32 + block parameters (fp32 masters; qkv/proj already latent-folded) -> [B,N,D] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, wqkv, bqkv, wproj, bproj, ln2_w, ln2_b, w1, b1, w2, b2, H, window, eps1, eps2,
+                cd):
+        B, N, D = x.shape
+        x2d = x.reshape(B * N, D)
+        if not x2d.is_contiguous():
+            x2d = x2d.contiguous()
+        c = (lambda t: t.detach().to(cd)) if cd != torch.float32 else (lambda t: t.detach())
+        f = lambda t: t.detach().float().contiguous()
+        wq_c, wp_c, w1_c, w2_c = c(wqkv), c(wproj), c(w1), c(w2)
+        outs = block_fwd(x2d.detach(), f(ln1_w), f(ln1_b), wq_c, f(bqkv), wp_c, f(bproj), f(ln2_w), f(ln2_b), w1_c,
+                         f(b1), w2_c, f(b2), B, N, H, window, eps1, eps2)
+        x3 = outs[0]
+        ctx.save_for_backward(x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *outs[1:])
+        ctx.dims = (B, N, H, window)
+        return x3.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *saved = ctx.saved_tensors
+        B, N, H, window = ctx.dims
+        D = x2d.shape[1]
+        g2d = g.reshape(B * N, D)
+        if g2d.dtype != torch.float32:
+            g2d = g2d.float()
+        outs = block_bwd(g2d, x2d, ln1_w.detach().float().contiguous(), wq_c, wp_c,
+                         ln2_w.detach().float().contiguous(), w1_c, w2_c, *saved, B, N, H, window)
+        dx = outs[0].view(B, N, D)
+        return (dx, *outs[1:], None, None, None, None, None)
+
+
+def fused_block(x, ln1, attn_folded, ln2, fc1, fc2, num_heads: int, window: int, compute_dtype: torch.dtype):
+    """attn_folded = (wqkv, bqkv, wproj, bproj) fp32 tensors (autograd-connected to qkv / proj / latent_proj)."""
+    wqkv, bqkv, wproj, bproj = attn_folded
+    return FusedBlockFn.apply(x, ln1.weight, ln1.bias, wqkv, bqkv, wproj, bproj, ln2.weight, ln2.bias, fc1.weight,
+                              fc1.bias, fc2.weight, fc2.bias, num_heads, window, ln1.eps, ln2.eps, compute_dtype)
+
+
+def fusable(x: Tensor, attn, mlp_dropout_p: float, training: bool, attention_mask, compute_dtype, hidden: int) -> bool:
+    """Conditions under which the block runs as the two fused ops (otherwise the caller composes the unfused ops)."""
+    if attention_mask is not None or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:
+        return False
+    if training and (mlp_dropout_p > 0 or attn.attn_dropout.p > 0):
+        return False
+    D = x.shape[-1]
+    if compute_dtype not in (torch.bfloat16, torch.float32):
+        return False
+    if attn.head_dim not in (16, 32, 64, 128) or D % 8 or D > 1024 or hidden % 8:
+        return False
+    if attn.window_size % 2 == 0 and x.shape[1] > attn.window_size:
+        return False
+    return True

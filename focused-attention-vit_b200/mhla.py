@@ -122,6 +122,17 @@ class MHLATransformerBlock(nn.Module):
         )
 
     def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from . import fused_block
+        cd = compute_dtype(x)
+        if fused_block.fusable(x, self.attn, self.mlp[2].p, self.training, attention_mask, cd,
+                               self.mlp[0].out_features):
+            a = self.attn
+            with torch.autocast("cuda", enabled=False):
+                folded = fold_latent(a.qkv.weight.float(), a.qkv.bias.float(), a.proj.weight.float(),
+                                     a.proj.bias.float(), a.latent_proj.weight.float(), a.latent_proj.bias.float(),
+                                     a.num_heads)
+                return fused_block.fused_block(x, self.norm1, folded, self.norm2, self.mlp[0], self.mlp[3],
+                                               a.num_heads, a.window_size, cd)
         x = x + self.attn(self.norm1(x), attention_mask)
         x = x + self.mlp(self.norm2(x))
         return x

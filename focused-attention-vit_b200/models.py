@@ -18,7 +18,8 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .mhla import MultiHeadLatentAttention
+from . import fused_block
+from .mhla import MultiHeadLatentAttention, compute_dtype, fold_latent
 from .sppp import PatchToSuperpixelMapper, SuperpixelPooling
 
 
@@ -84,6 +85,18 @@ class TransformerBlock(nn.Module):
         self.use_mhla = use_mhla
 
     def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.use_mhla:
+            cd = compute_dtype(x)
+            if fused_block.fusable(x, self.attn, self.mlp.dropout.p, self.training, attention_mask, cd,
+                                   self.mlp.fc1.out_features):
+                # whole block as two favit ops (LN, GEMMs with fused bias/GELU/residual, window attention)
+                a = self.attn
+                with torch.autocast("cuda", enabled=False):
+                    folded = fold_latent(a.qkv.weight.float(), a.qkv.bias.float(), a.proj.weight.float(),
+                                         a.proj.bias.float(), a.latent_proj.weight.float(),
+                                         a.latent_proj.bias.float(), a.num_heads)
+                    return fused_block.fused_block(x, self.norm1, folded, self.norm2, self.mlp.fc1, self.mlp.fc2,
+                                                   a.num_heads, a.window_size, cd)
         x_norm = self.norm1(x)
         if self.use_mhla:
             attn_output = self.attn(x_norm, attention_mask)

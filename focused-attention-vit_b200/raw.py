@@ -1,0 +1,108 @@
+"""Thin tensor-level wrappers over the C-ABI (no dispatcher, no autograd): the building blocks of the fused
+transformer-block ops in `fused_block.py`.  All tensors are CUDA, contiguous and 2-D unless stated."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], out_dtype: torch.dtype,
+               gelu: bool = False, save_preact: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    pre = torch.empty((M, N), dtype=x.dtype, device=x.device) if (gelu and save_preact) else None
+    rc = L.call("gemm_fwd", 2.0 * M * N * K, L.lib().favit_linear_fwd, _p(x), _p(w), _p(bias), _p(residual), _p(y),
+                _p(pre), M, N, K, K, K, N, N, _DT[x.dtype], _DT[out_dtype],
+                _DT[residual.dtype] if residual is not None else L.F32, L.EPI_GELU if gelu else L.EPI_NONE, _s())
+    L.check(rc, "favit_linear_fwd")
+    return y, pre
+
+
+def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype) -> Tensor:
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
+    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), M, N, K,
+                N, K, K, _DT[dy.dtype], _DT[out_dtype], L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _s())
+    L.check(rc, "favit_linear_dgrad")
+    return dx
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, want_bias: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    db = torch.empty((N,), dtype=torch.float32, device=dy.device) if want_bias else None
+    rc = L.call("gemm_wgrad", 2.0 * M * N * K, L.lib().favit_linear_wgrad, _p(dy), _p(x), _p(dw), _p(db), M, N, K, N, K,
+                K, _DT[dy.dtype], 0, _s())
+    L.check(rc, "favit_linear_wgrad")
+    return dw, db
+
+
+def ln_fwd(x: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float):
+    M, D = x.shape
+    y = torch.empty((M, D), dtype=out_dtype, device=x.device)
+    mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+    work = float(x.numel() * x.element_size() + y.numel() * y.element_size())
+    rc = L.call("ln_fwd", work, L.lib().favit_layernorm_fwd, _p(x), _DT[x.dtype], _p(gamma), _p(beta), _p(y),
+                _DT[out_dtype], _p(mean), _p(rstd), M, D, float(eps), _s())
+    L.check(rc, "favit_layernorm_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
+           want_bf16: bool):
+    """Returns (dx fp32, dx_bf16 or None, dgamma, dbeta)."""
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
+    dxb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    dg = torch.zeros((D,), dtype=torch.float32, device=x.device)
+    db = torch.zeros((D,), dtype=torch.float32, device=x.device)
+    work = float(dy.numel() * dy.element_size() + x.numel() * x.element_size() + dx.numel() * 4 +
+                 (dres.numel() * 4 if dres is not None else 0) + (dxb.numel() * 2 if want_bf16 else 0))
+    rc = L.call("ln_bwd", work, L.lib().favit_layernorm_bwd, _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(mean),
+                _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb), _p(dg), _p(db), M, D, _s())
+    L.check(rc, "favit_layernorm_bwd")
+    return dx, dxb, dg, db
+
+
+def attn_fwd(qkv: Tensor, B: int, N: int, H: int, hd: int, window: int):
+    """qkv [B*N, 3*H*hd] (packed, contiguous) -> out [B*N, H*hd], lse [B,H,N]."""
+    es = qkv.element_size()
+    out = torch.empty((B * N, H * hd), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    base = qkv.data_ptr()
+    rc = L.call("attn_fwd", 4.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_fwd, base, base + H * hd * es,
+                base + 2 * H * hd * es, None, _p(out), _p(lse), B, H, N, hd, window, float(hd) ** -0.5,
+                N * 3 * H * hd, 3 * H * hd, hd, _DT[qkv.dtype], 0.0, 0, _s())
+    L.check(rc, "favit_mhla_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, H: int, hd: int, window: int):
+    es = qkv.element_size()
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    off = H * hd * es
+    rc = L.call("attn_bwd", 8.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_bwd, base, base + off, base + 2 * off,
+                None, _p(out), _p(lse), _p(dout), dbase, dbase + off, dbase + 2 * off, _p(delta), B, H, N, hd, window,
+                float(hd) ** -0.5, N * 3 * H * hd, 3 * H * hd, hd, _DT[qkv.dtype], 0.0, 0, _s())
+    L.check(rc, "favit_mhla_attn_bwd")
+    return dqkv

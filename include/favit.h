@@ -119,6 +119,23 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
                         favit_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * LayerNorm around the attention / MLP — "next" row: nn.LayerNorm at models/vit_mhla.py:88,107
+ * (norm1 / norm2 of the block) and its autograd.  fp32 statistics; D % 4 == 0, D <= 1024.
+ *
+ * favit_layernorm_fwd: y[M,D] = (x - mean) * rstd * gamma + beta; mean / rstd [M] fp32 are saved for backward.
+ * favit_layernorm_bwd: dx[M,D] (fp32) = LN'(dy) + dres   (dres: fp32 gradient of the residual branch, may be NULL);
+ *      dx_bf16 (may be NULL) receives a bf16 copy of dx (the operand of the next dgrad / wgrad GEMM);
+ *      dgamma / dbeta [D] fp32 are ACCUMULATED into (zero them first); both NULL to skip.
+ * ---------------------------------------------------------------------------------------------- */
+int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const float* gamma, const float* beta, void* y,
+                        favit_dtype y_dtype, float* mean, float* rstd, int M, int D, float eps,
+                        favit_stream stream);
+
+int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const void* x, favit_dtype x_dtype,
+                        const float* mean, const float* rstd, const float* gamma, const float* dres, float* dx,
+                        void* dx_bf16, float* dgamma, float* dbeta, int M, int D, favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SPPP patch -> superpixel assignment — replaces PatchToSuperpixelMapper.map_patches,
  * models/sppp.py:91-128, for a whole batch in one call (the reference loops per image,
  * models/sppp_mhla.py:286-297).

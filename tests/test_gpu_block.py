@@ -1,0 +1,93 @@
+"""GPU parity of the fused transformer block (favit::block_fwd / block_bwd: LayerNorm, GEMMs with fused
+bias/GELU/residual, window attention) against the CPU oracle block, itself pinned to the reference by the golden
+fixtures; plus the LayerNorm kernels against torch."""
+import pytest
+import torch
+
+import oracle
+from oracle.models_oracle import block as oracle_block
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,D", [(37, 64), (300, 192), (1000, 384), (520, 768), (64, 1024)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_layernorm_fwd_bwd(M, D, out_dtype):
+    from favit_b200 import raw
+    torch.manual_seed(D)
+    x = (torch.randn(M, D, device="cuda") * 2 + 0.5)
+    gamma = torch.randn(D, device="cuda")
+    beta = torch.randn(D, device="cuda")
+    y, mean, rstd = raw.ln_fwd(x, gamma, beta, out_dtype, 1e-5)
+    xr = x.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+    assert_close(y, yr, out_dtype, "ln y")
+    assert_close(mean, xr.mean(dim=1), torch.float32, "mean")
+    dy = torch.randn(M, D, device="cuda").to(out_dtype)
+    dres = torch.randn(M, D, device="cuda")
+    yr.backward(dy.double())
+    dx, dxb, dg, db = raw.ln_bwd(dy, x, mean, rstd, gamma, dres, True)
+    assert_close(dx, xr.grad + dres.double(), torch.float32, "ln dx", factor=3.0)
+    assert_close(dxb, xr.grad + dres.double(), torch.bfloat16, "ln dx bf16")
+    assert_close(dg, gr.grad, torch.float32, "dgamma", factor=5.0)
+    assert_close(db, br.grad, torch.float32, "dbeta", factor=5.0)
+
+
+def _block_case(mode, B, N, D, H, W, ratio, seq_block):
+    from favit_b200.mhla import MHLATransformerBlock
+    from favit_b200.models import TransformerBlock
+    torch.manual_seed(B * N + D)
+    if seq_block:
+        blk = MHLATransformerBlock(embed_dim=D, num_heads=H, window_size=W, mlp_ratio=ratio)
+    else:
+        blk = TransformerBlock(embed_dim=D, num_heads=H, mlp_ratio=ratio, window_size=W, use_mhla=True)
+    for p in blk.parameters():          # non-trivial LayerNorm / bias values
+        if p.dim() == 1:
+            torch.nn.init.normal_(p, mean=0.3, std=0.5)
+    blk = blk.cuda()
+    x = torch.randn(B, N, D)
+    g = torch.randn(B, N, D)
+    dtype = torch.float32 if mode == "fp32" else torch.bfloat16
+    xc = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+        y = blk(xc)
+    assert y.dtype == torch.float32          # fp32 residual stream, like the reference under autocast
+    y.backward(g.cuda())
+    sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    yr = oracle_block(xr, sd, "", H, W)
+    yr.backward(g.double())
+    assert_close(y, yr, dtype, "block y")
+    assert_close(xc.grad, xr.grad, dtype, "block dx", factor=2.0)
+    for k, p in blk.named_parameters():
+        assert_close(p.grad, sd[k].grad, dtype, f"block d{k}", factor=3.0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,N,D,H,W,ratio,seq", [(2, 17, 128, 2, 7, 4.0, False), (3, 65, 192, 3, 7, 4.0, False),
+                                                 (2, 10, 64, 1, 3, 2.0, True), (1, 197, 768, 12, 7, 4.0, False),
+                                                 (2, 5, 128, 2, 7, 4.0, True)])
+def test_fused_block_matches_oracle(mode, B, N, D, H, W, ratio, seq):
+    from favit_b200 import fused_block
+    calls = []
+    orig = fused_block.fused_block
+    fused_block.fused_block = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        _block_case(mode, B, N, D, H, W, ratio, seq)
+    finally:
+        fused_block.fused_block = orig
+    assert calls, "the fused path was not taken"
+
+
+def test_fused_and_unfused_paths_agree():
+    """The unfused composition (mask / dropout cases) and the fused ops are the same math."""
+    from favit_b200.models import TransformerBlock
+    torch.manual_seed(5)
+    blk = TransformerBlock(embed_dim=128, num_heads=2, window_size=7, use_mhla=True).cuda()
+    x = torch.randn(2, 33, 128, device="cuda")
+    y_fused = blk(x)
+    mask = torch.ones(2, 33, 33, device="cuda")      # an all-ones mask forces the unfused path
+    y_unfused = blk(x, mask)
+    assert_close(y_unfused, y_fused, torch.float32, "fused vs unfused")
