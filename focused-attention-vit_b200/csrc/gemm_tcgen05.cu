@@ -15,8 +15,9 @@
 // Either way a pipeline stage holds a 128 x 64 slab of A and a BN x 64 slab of B in the canonical
 // SWIZZLE_128B layout, written by TMA and read by the UMMA shared-memory descriptors.
 //
-// Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (each owns 32 TMEM lanes = 32 rows of the tile).
+// Warp roles (384 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warps 4..11 = epilogue: warp w may touch TMEM lanes 32*(w%4).. (32 rows of the tile); the two warps of a
+// lane quarter split the tile's columns, so the bias/GELU/residual math drains a tile in half the time.
 // TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Split-K work units (weight gradients: few output tiles, very long reduction) accumulate with fp32
 // atomics (red.global.add.f32) into an output the caller has zeroed or wants to accumulate into.
@@ -36,7 +37,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr uint32_t kSlabBytes = 64 * 128;  // MN-major: 64 reduction rows x 128 B
 
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
@@ -157,10 +159,34 @@ struct KParams {
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers: 32 consecutive columns of one row
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load32(const void* base, int dtype, int64_t off, bool vec, int ncols, float (&f)[32]) {
+// `vec`: 0 = scalar (ragged / misaligned), 1 = 128-bit accesses, 2 = 256-bit accesses (each lane moves whole 32-byte
+// sectors of its own row, so no partially written sector ever reaches L2).
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void load32(const void* base, int dtype, int64_t off, int vec, int ncols, float (&f)[32]) {
   if (dtype == FAVIT_BF16) {
     const __nv_bfloat16* p = (const __nv_bfloat16*)base + off;
-    if (vec) {
+    if (vec == 2) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        uint32_t r[8];
+        ldg256(p + 16 * i, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[16 * i + 2 * j] = __uint_as_float(r[j] << 16);
+          f[16 * i + 2 * j + 1] = __uint_as_float(r[j] & 0xffff0000u);
+        }
+      }
+    } else if (vec == 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float t[8];
@@ -174,7 +200,15 @@ __device__ __forceinline__ void load32(const void* base, int dtype, int64_t off,
     }
   } else {
     const float* p = (const float*)base + off;
-    if (vec) {
+    if (vec == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t r[8];
+        ldg256(p + 8 * i, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * i + j] = __uint_as_float(r[j]);
+      }
+    } else if (vec == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
@@ -187,10 +221,18 @@ __device__ __forceinline__ void load32(const void* base, int dtype, int64_t off,
   }
 }
 
-__device__ __forceinline__ void store32(void* base, int dtype, int64_t off, bool vec, int ncols, const float (&f)[32]) {
+__device__ __forceinline__ void store32(void* base, int dtype, int64_t off, int vec, int ncols, const float (&f)[32]) {
   if (dtype == FAVIT_BF16) {
     __nv_bfloat16* p = (__nv_bfloat16*)base + off;
-    if (vec) {
+    if (vec == 2) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = pack_bf16x2(f[16 * i + 2 * j], f[16 * i + 2 * j + 1]);
+        stg256(p + 16 * i, r);
+      }
+    } else if (vec == 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
@@ -207,7 +249,15 @@ __device__ __forceinline__ void store32(void* base, int dtype, int64_t off, bool
     }
   } else {
     float* p = (float*)base + off;
-    if (vec) {
+    if (vec == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(f[8 * i + j]);
+        stg256(p + 8 * i, r);
+      }
+    } else if (vec == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(p + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -219,9 +269,11 @@ __device__ __forceinline__ void store32(void* base, int dtype, int64_t off, bool
   }
 }
 
-__device__ __forceinline__ bool vec_ok(const void* base, int dtype, int64_t ld) {
-  const int al = (dtype == FAVIT_BF16) ? 8 : 4;
-  return (((uintptr_t)base) % 16 == 0) && (ld % al == 0);
+__device__ __forceinline__ int vec_ok(const void* base, int dtype, int64_t ld) {
+  const int es = (dtype == FAVIT_BF16) ? 2 : 4;
+  if ((((uintptr_t)base) % 32 == 0) && ((ld * es) % 32 == 0)) return 2;
+  if ((((uintptr_t)base) % 16 == 0) && ((ld * es) % 16 == 0)) return 1;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -263,7 +315,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), kEpiWarps);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -347,13 +399,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const Epilogue& e = p.epi;
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int wq = warp & 3;              // TMEM lane quarter this warp may access
+    const int chalf = (warp - 4) >> 2;     // which half of the tile's columns this warp drains
+    constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool c_vec = vec_ok(e.c, e.c_dtype, e.ldc);
-    const bool r_vec = e.residual ? vec_ok(e.residual, e.res_dtype, e.ldres) : false;
-    const bool x_vec = e.aux ? vec_ok(e.aux, FAVIT_BF16, e.ldaux) : false;
-    const bool o_vec = e.aux_out ? vec_ok(e.aux_out, FAVIT_BF16, e.ldaux) : false;
+    const int c_vec = vec_ok(e.c, e.c_dtype, e.ldc);
+    const int r_vec = e.residual ? vec_ok(e.residual, e.res_dtype, e.ldres) : 0;
+    const int x_vec = e.aux ? vec_ok(e.aux, FAVIT_BF16, e.ldaux) : 0;
+    const int o_vec = e.aux_out ? vec_ok(e.aux_out, FAVIT_BF16, e.ldaux) : 0;
+    const bool b_vec = e.bias ? (((uintptr_t)e.bias) % 16 == 0) : false;
     const bool atomic = (p.splits > 1) || e.accumulate;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int tile = u / p.splits;
@@ -363,7 +418,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m0 + wq * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * kColsPerWarp; c0 < (chalf + 1) * kColsPerWarp; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_wait_ld();
@@ -376,32 +431,48 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (atomic) {
             float* cp = (float*)e.c + (int64_t)row * e.ldc + col;
+            if (full && c_vec >= 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols) atomicAdd(cp + i, v[i]);
-          } else {
-            if (e.bias) {
+              for (int i = 0; i < 8; ++i)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * i), "f"(v[4 * i]),
+                             "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                             : "memory");
+            } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < ncols) v[i] += __ldg(e.bias + col + i);
+                if (i < ncols) atomicAdd(cp + i, v[i]);
+            }
+          } else {
+            if (e.bias) {
+              if (full && b_vec) {   // every lane reads the same 128 bytes: broadcast loads
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col) + i);
+                  v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols) v[i] += __ldg(e.bias + col + i);
+              }
             }
             if (e.act == FAVIT_EPI_GELU) {
-              if (e.aux_out) store32(e.aux_out, FAVIT_BF16, (int64_t)row * e.ldaux + col, full && o_vec, ncols, v);
+              if (e.aux_out) store32(e.aux_out, FAVIT_BF16, (int64_t)row * e.ldaux + col, full ? o_vec : 0, ncols, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
             } else if (e.act == FAVIT_EPI_DGELU_MUL) {
               float x[32];
-              load32(e.aux, FAVIT_BF16, (int64_t)row * e.ldaux + col, full && x_vec, ncols, x);
+              load32(e.aux, FAVIT_BF16, (int64_t)row * e.ldaux + col, full ? x_vec : 0, ncols, x);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= dgelu_erf(x[i]);
+              for (int i = 0; i < 32; ++i) v[i] *= dgelu_fast(x[i]);
             }
             if (e.residual) {
               float x[32];
-              load32(e.residual, e.res_dtype, (int64_t)row * e.ldres + col, full && r_vec, ncols, x);
+              load32(e.residual, e.res_dtype, (int64_t)row * e.ldres + col, full ? r_vec : 0, ncols, x);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += x[i];
             }
-            store32(e.c, e.c_dtype, (int64_t)row * e.ldc + col, full && c_vec, ncols, v);
+            store32(e.c, e.c_dtype, (int64_t)row * e.ldc + col, full ? c_vec : 0, ncols, v);
           }
         }
       }
@@ -489,26 +560,36 @@ int gemm_bf16(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int
   const int m_tiles = ceil_div(M, BM);
   const int k_blocks = ceil_div(K, BK);
 
-  // tile width: the widest BN whose tile count still fills the machine
-  int bn = force_bn;
-  if (bn == 0) {
-    bn = 256;
-    if (N <= 64) bn = 64;
-    else if (N <= 128) bn = 128;
-    else if ((int64_t)m_tiles * ceil_div(N, 256) < sms) bn = ((int64_t)m_tiles * ceil_div(N, 128) < sms && N % 128 != 0) ? 64 : 128;
+  // Tile width and split-K factor from a small cost model (cycles per CTA, slowest CTA decides):
+  //   a k-block costs 4 MMAs of max(128, BN/2)-ish cycles, but BN < 256 is shared-memory-bandwidth bound
+  //   (A is re-read for fewer output columns), so narrower tiles are only worth it when they fill idle SMs.
+  const bool can_split = epi.c_dtype == FAVIT_F32 && epi.bias == nullptr && epi.act == FAVIT_EPI_NONE &&
+                         epi.residual == nullptr && epi.split_ok;
+  int bn = force_bn, splits = force_splits > 0 ? force_splits : 1;
+  if (force_bn == 0 || force_splits == 0) {
+    const int cand[3] = {256, 128, 64};
+    const double kb_cycles[3] = {512.0, 300.0, 200.0};
+    const double fixed[3] = {2200.0, 1300.0, 900.0};
+    double best = 1e30;
+    for (int c = 0; c < 3; ++c) {
+      if (force_bn && cand[c] != force_bn) continue;
+      if (!force_bn && c > 0 && N <= cand[c]) {
+        // a narrower tile than N needs is pointless unless the wider one does not exist
+      }
+      const int64_t t = (int64_t)m_tiles * ceil_div(N, cand[c]);
+      const int smax = force_splits > 0 ? force_splits : (can_split ? min(32, max(1, k_blocks / 4)) : 1);
+      for (int sp = (force_splits > 0 ? force_splits : 1); sp <= smax; ++sp) {
+        const int kps = ceil_div(k_blocks, sp);
+        const int sp_eff = ceil_div(k_blocks, kps);
+        const double waves = (double)ceil_div64(t * sp_eff, sms);
+        const double cost = waves * (kps * kb_cycles[c] + fixed[c] * (sp_eff > 1 ? 1.5 : 1.0));
+        if (cost < best) { best = cost; bn = cand[c]; splits = sp_eff; }
+      }
+    }
   }
   FAVIT_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm_tcgen05: BN must be 64, 128 or 256");
   const int n_tiles = ceil_div(N, bn);
   const int64_t tiles = (int64_t)m_tiles * n_tiles;
-
-  const bool can_split = epi.c_dtype == FAVIT_F32 && epi.bias == nullptr && epi.act == FAVIT_EPI_NONE &&
-                         epi.residual == nullptr && epi.split_ok;
-  int splits = 1;
-  if (force_splits > 0) {
-    splits = force_splits;
-  } else if (can_split && tiles < sms && k_blocks >= 8) {
-    splits = (int)min((int64_t)k_blocks / 4, ceil_div64(2 * (int64_t)sms, tiles));
-  }
   if (splits < 1) splits = 1;
   FAVIT_CHECK_ARG(splits == 1 || can_split, "gemm_tcgen05: split-K needs a plain fp32 accumulate epilogue");
   int kb_per_split = ceil_div(k_blocks, splits);

@@ -50,7 +50,8 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const fl
 
 // D % 4 == 0, D <= 1024.  Lane l owns float4 chunks l, l+32, ... (coalesced 512-byte warp accesses).
 template <typename TX, typename TY, int NV>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const TY* __restrict__ delta,
+                                                     TX* __restrict__ xsum, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, TY* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int D,
                                                      float eps) {
@@ -64,10 +65,29 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < nvec) {
-      load4(xr + 4 * c, v[i]);
-      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    if (c < nvec) load4(xr + 4 * c, v[i]);
+  }
+  if (delta) {  // residual add fused in front of the norm: xsum = x + delta is the new residual stream
+    float d[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) load4(delta + (int64_t)row * D + 4 * c, d[i]);
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[i][e] += d[i][e];
+        store4(xsum + (int64_t)row * D + 4 * c, v[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
   }
   const float mu = warp_sum(s) / (float)D;
   float q = 0.f;
@@ -102,63 +122,82 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
   }
 }
 
-// Persistent over rows: warp w handles rows w, w + total_warps, ...; per-lane dgamma/dbeta partials stay in registers
-// and are combined through shared memory, then one atomic per column per CTA.
-template <typename TX, typename TDY, int NV>
+// Two warps per row (each owns one half of the columns, NVH float4 per lane), two rows in flight per 128-thread CTA,
+// persistent over rows.  Halving the per-thread column count keeps the dgamma/dbeta partials plus a whole row of
+// operands in registers without spilling, so every load of a row is in flight at once.  The two row sums are exchanged
+// between the warps of a pair through shared memory and a 64-thread named barrier (parity double-buffered).
+template <typename TX, typename TDY, int NVH>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
                                                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
                                                      int D) {
-  extern __shared__ float s_red[];  // [2][warps][D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  extern __shared__ float s_red[];          // [2][pairs][D] for the final dgamma/dbeta combine
+  __shared__ float2 s_xchg[2][2][2];        // [parity][pair][half] = (sum g, sum g*xhat)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pair = warp >> 1, half = warp & 1, npairs = blockDim.x >> 6;
   const int nvec = D >> 2;
-  float dg[NV][4], db[NV][4];
+  const int nvh = (nvec + 1) >> 1;           // float4 chunks per half
+  const int cbase = half * nvh;
+  const int cend = min(nvec, cbase + nvh);
+  float dg[NVH][4], db[NVH][4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NVH; ++i)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
   const float invD = 1.f / (float)D;
-  for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
+  int parity = 0;
+  for (int row = blockIdx.x * npairs + pair; row < M; row += gridDim.x * npairs, parity ^= 1) {
     const TX* xr = x + (int64_t)row * D;
     const TDY* dyr = dy + (int64_t)row * D;
+    float xh[NVH][4], gy[NVH][4], rr[NVH][4];
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) {
+      const int c = cbase + lane + 32 * i;
+      if (c < cend) {
+        load4(xr + 4 * c, xh[i]);
+        load4(dyr + 4 * c, gy[i]);
+        if (dres) load4(dres + (int64_t)row * D + 4 * c, rr[i]);
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV][4], gy[NV][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        float xv[4], dv[4], g[4];
-        load4(xr + 4 * c, xv);
-        load4(dyr + 4 * c, dv);
+    for (int i = 0; i < NVH; ++i) {
+      const int c = cbase + lane + 32 * i;
+      if (c < cend) {
+        float g[4];
         load4(gamma + 4 * c, g);  // L1-resident
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xh[i][e] = (xv[e] - mu) * rs;
-          gy[i][e] = dv[e] * g[e];
+          const float xv = (xh[i][e] - mu) * rs;
+          const float dv = gy[i][e];
+          xh[i][e] = xv;
+          gy[i][e] = dv * g[e];
           s1 += gy[i][e];
-          s2 = fmaf(gy[i][e], xh[i][e], s2);
-          dg[i][e] = fmaf(dv[e], xh[i][e], dg[i][e]);
-          db[i][e] += dv[e];
+          s2 = fmaf(gy[i][e], xv, s2);
+          dg[i][e] = fmaf(dv, xv, dg[i][e]);
+          db[i][e] += dv;
         }
       }
     }
-    s1 = warp_sum(s1) * invD;
-    s2 = warp_sum(s2) * invD;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) s_xchg[parity][pair][half] = make_float2(s1, s2);
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+    const float2 other = s_xchg[parity][pair][half ^ 1];
+    s1 = (s1 + other.x) * invD;
+    s2 = (s2 + other.y) * invD;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
+    for (int i = 0; i < NVH; ++i) {
+      const int c = cbase + lane + 32 * i;
+      if (c < cend) {
         float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
-        if (dres) {
-          float r[4];
-          load4(dres + (int64_t)row * D + 4 * c, r);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += r[e];
+        for (int e = 0; e < 4; ++e) {
+          o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
+          if (dres) o[e] += rr[i][e];
         }
         store4(dx + (int64_t)row * D + 4 * c, o);
         if (dx_bf16) store4(dx_bf16 + (int64_t)row * D + 4 * c, o);
@@ -167,22 +206,22 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
   }
   if (dgamma == nullptr) return;
   float* sg = s_red;
-  float* sb = s_red + (size_t)nwarps * D;
+  float* sb = s_red + (size_t)npairs * D;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
+  for (int i = 0; i < NVH; ++i) {
+    const int c = cbase + lane + 32 * i;
+    if (c < cend) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        sg[warp * D + 4 * c + e] = dg[i][e];
-        sb[warp * D + 4 * c + e] = db[i][e];
+        sg[pair * D + 4 * c + e] = dg[i][e];
+        sb[pair * D + 4 * c + e] = db[i][e];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int w = 0; w < nwarps; ++w) {
+    for (int w = 0; w < npairs; ++w) {
       a += sg[w * D + c];
       b += sb[w * D + c];
     }
@@ -196,10 +235,11 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
 
 using namespace favit;
 
-extern "C" int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const float* gamma, const float* beta, void* y,
-                                   favit_dtype y_dtype, float* mean, float* rstd, int M, int D, float eps,
-                                   favit_stream stream) {
+extern "C" int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const void* delta, void* xsum,
+                                   const float* gamma, const float* beta, void* y, favit_dtype y_dtype, float* mean,
+                                   float* rstd, int M, int D, float eps, favit_stream stream) {
   FAVIT_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  FAVIT_CHECK_ARG((delta == nullptr) == (xsum == nullptr), "layernorm_fwd: delta and xsum come together");
   FAVIT_CHECK_ARG(M > 0 && D > 0, "layernorm_fwd: M, D must be positive");
   if (D % 4 != 0 || D > 128 * kMaxVec) {
     set_error("layernorm_fwd: D=%d unsupported (needs D %% 4 == 0 and D <= %d)", D, 128 * kMaxVec);
@@ -211,7 +251,8 @@ extern "C" int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)ceil_div(M, 8);
 #define LN_FWD_NV(TX, TY, NV) \
-  ln_fwd_kernel<TX, TY, NV><<<blocks, 256, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, M, D, eps)
+  ln_fwd_kernel<TX, TY, NV><<<blocks, 256, 0, st>>>((const TX*)x, (const TY*)delta, (TX*)xsum, gamma, beta, (TY*)y, \
+                                                    mean, rstd, M, D, eps)
 #define LN_FWD(TX, TY)                            \
   do {                                            \
     if (D <= 256) LN_FWD_NV(TX, TY, 2);           \
@@ -245,18 +286,18 @@ extern "C" int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const v
     return FAVIT_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int warps = 4;
-  const size_t smem = (size_t)2 * warps * D * sizeof(float);  // <= 32 KiB
-  const unsigned blocks = (unsigned)max(1, min(ceil_div(M, warps), 8 * num_sms()));
-#define LN_BWD_NV(TX, TDY, NV)                                                                                   \
-  ln_bwd_kernel<TX, TDY, NV><<<blocks, warps * 32, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
-                                                               dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, D)
+  const int pairs = 2;                                          // rows in flight per CTA (2 warps each)
+  const size_t smem = (size_t)2 * pairs * D * sizeof(float);   // <= 16 KiB
+  const unsigned blocks = (unsigned)max(1, min(ceil_div(M, pairs), 6 * num_sms()));
+#define LN_BWD_NV(TX, TDY, NVH)                                                                                  \
+  ln_bwd_kernel<TX, TDY, NVH><<<blocks, pairs * 64, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
+                                                                dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, D)
 #define LN_BWD(TX, TDY)                           \
   do {                                            \
-    if (D <= 256) LN_BWD_NV(TX, TDY, 2);          \
-    else if (D <= 512) LN_BWD_NV(TX, TDY, 4);     \
-    else if (D <= 768) LN_BWD_NV(TX, TDY, 6);     \
-    else LN_BWD_NV(TX, TDY, 8);                   \
+    if (D <= 256) LN_BWD_NV(TX, TDY, 1);          \
+    else if (D <= 512) LN_BWD_NV(TX, TDY, 2);     \
+    else if (D <= 768) LN_BWD_NV(TX, TDY, 3);     \
+    else LN_BWD_NV(TX, TDY, 4);                   \
   } while (0)
   if (x_dtype == FAVIT_F32 && dy_dtype == FAVIT_BF16) LN_BWD(float, __nv_bfloat16);
   else if (x_dtype == FAVIT_F32 && dy_dtype == FAVIT_F32) LN_BWD(float, float);

@@ -17,6 +17,15 @@
 #include "favit_common.cuh"
 
 namespace favit {
+
+// tensor-core tile path (mhla_window_attn_mma.cu)
+bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* mask);
+int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
+                 int window, float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+int attn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                 void* dq, void* dk, void* dv, float* delta, int B, int H, int N, int hd, int window, float scale,
+                 int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -364,6 +373,9 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse, "mhla_attn_fwd: null out/lse");
+  if (attn_mma_applicable(hd, window, dtype, mask))
+    return attn_mma_fwd(q, k, v, out, lse, B, H, N, hd, window, scale, stride_b, stride_n, stride_h,
+                        (cudaStream_t)stream);
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FAVIT_BF16) {
@@ -382,6 +394,9 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse && dout && dq && dk && dv && delta, "mhla_attn_bwd: null pointer");
+  if (attn_mma_applicable(hd, window, dtype, mask))
+    return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, B, H, N, hd, window, scale, stride_b, stride_n,
+                        stride_h, (cudaStream_t)stream);
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FAVIT_BF16) {

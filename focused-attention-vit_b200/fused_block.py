@@ -41,8 +41,10 @@ def block_fwd(x: Tensor, ln1_w: Tensor, ln1_b: Tensor, wqkv: Tensor, bqkv: Tenso
     xn, mu1, rs1 = raw.ln_fwd(x, ln1_w, ln1_b, cd, eps1)
     qkv, _ = raw.linear_fwd(xn, wqkv, bqkv, None, cd)
     o, lse = raw.attn_fwd(qkv, B, N, H, hd, window)
-    x2, _ = raw.linear_fwd(o, wproj, bproj, x, torch.float32)
-    xn2, mu2, rs2 = raw.ln_fwd(x2, ln2_w, ln2_b, cd, eps2)
+    # the attention branch joins the fp32 residual stream inside the LayerNorm kernel (coalesced row accesses) rather
+    # than in the GEMM epilogue (one thread per row): same bytes, moved to where they stream at HBM speed
+    a, _ = raw.linear_fwd(o, wproj, bproj, None, cd)
+    xn2, mu2, rs2, x2 = raw.ln_fwd(x, ln2_w, ln2_b, cd, eps2, delta=a)
     h, hpre = raw.linear_fwd(xn2, w1, b1, None, cd, gelu=True, save_preact=True)
     x3, _ = raw.linear_fwd(h, w2, b2, x2, torch.float32)
     return [x3, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h]

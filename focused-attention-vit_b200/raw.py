@@ -54,15 +54,22 @@ def linear_wgrad(dy: Tensor, x: Tensor, want_bias: bool = True) -> Tuple[Tensor,
     return dw, db
 
 
-def ln_fwd(x: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float):
+def ln_fwd(x: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: float,
+           delta: Optional[Tensor] = None):
+    """Returns (y, mean, rstd) or, with delta (out_dtype), (y, mean, rstd, xsum = x + delta)."""
     M, D = x.shape
     y = torch.empty((M, D), dtype=out_dtype, device=x.device)
+    xsum = torch.empty_like(x) if delta is not None else None
     mean = torch.empty((M,), dtype=torch.float32, device=x.device)
     rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
     work = float(x.numel() * x.element_size() + y.numel() * y.element_size())
-    rc = L.call("ln_fwd", work, L.lib().favit_layernorm_fwd, _p(x), _DT[x.dtype], _p(gamma), _p(beta), _p(y),
-                _DT[out_dtype], _p(mean), _p(rstd), M, D, float(eps), _s())
+    if delta is not None:
+        work += float(delta.numel() * delta.element_size() + xsum.numel() * xsum.element_size())
+    rc = L.call("ln_fwd", work, L.lib().favit_layernorm_fwd, _p(x), _DT[x.dtype], _p(delta), _p(xsum), _p(gamma),
+                _p(beta), _p(y), _DT[out_dtype], _p(mean), _p(rstd), M, D, float(eps), _s())
     L.check(rc, "favit_layernorm_fwd")
+    if delta is not None:
+        return y, mean, rstd, xsum
     return y, mean, rstd
 
 

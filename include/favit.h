@@ -123,13 +123,16 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
  * (norm1 / norm2 of the block) and its autograd.  fp32 statistics; D % 4 == 0, D <= 1024.
  *
  * favit_layernorm_fwd: y[M,D] = (x - mean) * rstd * gamma + beta; mean / rstd [M] fp32 are saved for backward.
+ *      With delta != NULL (dtype = y_dtype) the residual add in front of the norm is fused: xsum = x + delta is
+ *      written (x's dtype) and normalised — the attention output joins the residual stream here instead of in
+ *      the GEMM epilogue (models/vit_mhla.py:104-107).
  * favit_layernorm_bwd: dx[M,D] (fp32) = LN'(dy) + dres   (dres: fp32 gradient of the residual branch, may be NULL);
  *      dx_bf16 (may be NULL) receives a bf16 copy of dx (the operand of the next dgrad / wgrad GEMM);
  *      dgamma / dbeta [D] fp32 are ACCUMULATED into (zero them first); both NULL to skip.
  * ---------------------------------------------------------------------------------------------- */
-int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const float* gamma, const float* beta, void* y,
-                        favit_dtype y_dtype, float* mean, float* rstd, int M, int D, float eps,
-                        favit_stream stream);
+int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const void* delta, void* xsum, const float* gamma,
+                        const float* beta, void* y, favit_dtype y_dtype, float* mean, float* rstd, int M, int D,
+                        float eps, favit_stream stream);
 
 int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const void* x, favit_dtype x_dtype,
                         const float* mean, const float* rstd, const float* gamma, const float* dres, float* dx,

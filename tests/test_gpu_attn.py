@@ -53,8 +53,9 @@ def _run(B, H, N, hd, W, use_mask, dtype):
     assert_close(out, o_ref, dtype, "out")
     assert_close(lse, lse_ref, torch.float32 if dtype == torch.float32 else dtype, "lse")
     assert_close(qc.grad, q64.grad, dtype, "dqkv")
+    scale = q64.grad.abs().max().item()      # dq is analytically 0 when every slot of a window is the same key (N = 1)
     for i, nm in enumerate("qkv"):
-        assert_close(qc.grad[:, :, i], q64.grad[:, :, i], dtype, "d" + nm, factor=2.0)
+        assert_close(qc.grad[:, :, i], q64.grad[:, :, i], dtype, "d" + nm, factor=2.0, floor=1e-2 * scale)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "B{}H{}N{}hd{}W{}{}".format(*c[:5], "m" if c[5] else ""))

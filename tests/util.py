@@ -14,15 +14,16 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
 
 
-def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
-    """max |got - ref| / max |ref|  (fp64, on the CPU)."""
+def rel_err(got: torch.Tensor, ref: torch.Tensor, floor: float = 1e-30) -> float:
+    """max |got - ref| / max(max |ref|, floor)  (fp64, on the CPU).  `floor` is the magnitude below which the reference
+    counts as zero (e.g. a gradient that is analytically 0: the scale of its sibling gradients)."""
     g = got.detach().double().cpu()
     r = ref.detach().double().cpu()
     assert g.shape == r.shape, (g.shape, r.shape)
-    denom = max(r.abs().max().item(), 1e-30)
+    denom = max(r.abs().max().item(), floor)
     return (g - r).abs().max().item() / denom
 
 
-def assert_close(got, ref, dtype, what="", factor=1.0):
-    e = rel_err(got, ref)
+def assert_close(got, ref, dtype, what="", factor=1.0, floor=1e-30):
+    e = rel_err(got, ref, floor)
     assert e <= TOL[dtype] * factor, f"{what}: rel err {e:.3e} > {TOL[dtype] * factor:.1e} ({dtype})"

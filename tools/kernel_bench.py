@@ -1,0 +1,121 @@
+"""Per-kernel microbenchmark at the shapes of a workload (default: ViT-B/16, 256 images -> M = 50432 tokens).
+CUDA-event timing, inputs cycled through several buffers so that nothing stays L2-resident between iterations.
+
+    python tools/kernel_bench.py [--M 50432] [--D 768] [--H 12] [--N 197] [--iters 20] [--only gemm|ln|attn]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import favit_b200  # noqa: F401
+from favit_b200 import raw
+
+PEAK_TF, PEAK_GB = 1683.8, 6451.5
+try:
+    _p = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    PEAK_TF, PEAK_GB = _p["bf16_tflops"], _p["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timeit(fn, iters, nbuf):
+    for i in range(3):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % nbuf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=256)
+    ap.add_argument("--N", type=int, default=197)
+    ap.add_argument("--D", type=int, default=768)
+    ap.add_argument("--H", type=int, default=12)
+    ap.add_argument("--W", type=int, default=7)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    B, N, D, H = a.B, a.N, a.D, a.H
+    M = B * N
+    hid = 4 * D
+    dev = "cuda"
+    bf = torch.bfloat16
+    nbuf = 3
+    rnd = lambda *s: [torch.randn(*s, device=dev).to(bf) for _ in range(nbuf)]
+    rndf = lambda *s: [torch.randn(*s, device=dev) for _ in range(nbuf)]
+    rows = []
+
+    def rec(name, us, flops=None, bytes_=None):
+        r = {"kernel": name, "us": round(us, 1)}
+        if flops:
+            r["tflops"] = round(flops / us / 1e6, 1)
+            r["frac_burst_peak"] = round(r["tflops"] / PEAK_TF, 3)
+        if bytes_:
+            r["gbps"] = round(bytes_ / us / 1e3, 1)
+            r["frac_hbm"] = round(r["gbps"] / PEAK_GB, 3)
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+
+    if a.only in ("", "gemm"):
+        xD, xH = rnd(M, D), rnd(M, hid)
+        x3D = rnd(M, 3 * D)
+        resf = rndf(M, D)
+        wqkv, wproj = torch.randn(3 * D, D, device=dev).to(bf), torch.randn(D, D, device=dev).to(bf)
+        w1, w2 = torch.randn(hid, D, device=dev).to(bf), torch.randn(D, hid, device=dev).to(bf)
+        b3, bD, bH = torch.randn(3 * D, device=dev), torch.randn(D, device=dev), torch.randn(hid, device=dev)
+        f = lambda m, n, k: 2.0 * m * n * k
+        rec("qkv  fwd  bias            ", timeit(lambda i: raw.linear_fwd(xD[i], wqkv, b3, None, bf), a.iters, nbuf), f(M, 3 * D, D))
+        rec("qkv  fwd  nobias          ", timeit(lambda i: raw.linear_fwd(xD[i], wqkv, None, None, bf), a.iters, nbuf), f(M, 3 * D, D))
+        rec("proj fwd  bias+res f32out ", timeit(lambda i: raw.linear_fwd(xD[i], wproj, bD, resf[i], torch.float32), a.iters, nbuf), f(M, D, D))
+        rec("proj fwd  bias bf16out    ", timeit(lambda i: raw.linear_fwd(xD[i], wproj, bD, None, bf), a.iters, nbuf), f(M, D, D))
+        rec("fc1  fwd  bias+gelu+preact", timeit(lambda i: raw.linear_fwd(xD[i], w1, bH, None, bf, True, True), a.iters, nbuf), f(M, hid, D))
+        rec("fc1  fwd  bias only       ", timeit(lambda i: raw.linear_fwd(xD[i], w1, bH, None, bf), a.iters, nbuf), f(M, hid, D))
+        rec("fc2  fwd  bias+res f32out ", timeit(lambda i: raw.linear_fwd(xH[i], w2, bD, resf[i], torch.float32), a.iters, nbuf), f(M, D, hid))
+        rec("fc2  dgrad dgelu          ", timeit(lambda i: raw.linear_dgrad(xD[i], w2, xH[i], bf), a.iters, nbuf), f(M, D, hid))
+        rec("fc2  dgrad plain          ", timeit(lambda i: raw.linear_dgrad(xD[i], w2, None, bf), a.iters, nbuf), f(M, D, hid))
+        rec("fc1  dgrad                ", timeit(lambda i: raw.linear_dgrad(xH[i], w1, None, bf), a.iters, nbuf), f(M, D, hid))
+        rec("qkv  dgrad                ", timeit(lambda i: raw.linear_dgrad(x3D[i], wqkv, None, bf), a.iters, nbuf), f(M, 3 * D, D))
+        rec("proj dgrad                ", timeit(lambda i: raw.linear_dgrad(xD[i], wproj, None, bf), a.iters, nbuf), f(M, D, D))
+        rec("fc2  wgrad+db             ", timeit(lambda i: raw.linear_wgrad(xD[i], xH[i]), a.iters, nbuf), f(M, D, hid))
+        rec("fc1  wgrad+db             ", timeit(lambda i: raw.linear_wgrad(xH[i], xD[i]), a.iters, nbuf), f(M, D, hid))
+        rec("qkv  wgrad+db             ", timeit(lambda i: raw.linear_wgrad(x3D[i], xD[i]), a.iters, nbuf), f(M, 3 * D, D))
+        rec("proj wgrad+db             ", timeit(lambda i: raw.linear_wgrad(xD[i], xD[(i + 1) % nbuf]), a.iters, nbuf), f(M, D, D))
+        rec("proj wgrad no db          ", timeit(lambda i: raw.linear_wgrad(xD[i], xD[(i + 1) % nbuf], False), a.iters, nbuf), f(M, D, D))
+        ref = timeit(lambda i: torch.matmul(xD[i], wqkv.t()), a.iters, nbuf)
+        rec("cuBLAS qkv fwd (reference)", ref, f(M, 3 * D, D))
+        ref = timeit(lambda i: torch.matmul(xH[i], w2.t()), a.iters, nbuf)
+        rec("cuBLAS fc2 fwd (reference)", ref, f(M, D, hid))
+        del xD, xH, x3D, resf
+    if a.only in ("", "ln"):
+        xf = rndf(M, D)
+        g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+        rec("ln fwd f32->bf16", timeit(lambda i: raw.ln_fwd(xf[i], g, b, bf, 1e-5), a.iters, nbuf), None, M * D * 6.0)
+        y, mean, rstd = raw.ln_fwd(xf[0], g, b, bf, 1e-5)
+        dy = rnd(M, D)
+        rec("ln bwd (+dres, bf16 copy)", timeit(lambda i: raw.ln_bwd(dy[i], xf[0], mean, rstd, g, xf[(i + 1) % nbuf], True),
+                                                 a.iters, nbuf), None, M * D * (2 + 4 + 4 + 4 + 2.0))
+        del xf, dy
+    if a.only in ("", "attn"):
+        hd = D // H
+        qkv = rnd(M, 3 * D)
+        do = rnd(M, D)
+        rec("attn fwd", timeit(lambda i: raw.attn_fwd(qkv[i], B, N, H, hd, a.W), a.iters, nbuf), None, 4.0 * M * D * 2)
+        o, lse = raw.attn_fwd(qkv[0], B, N, H, hd, a.W)
+        rec("attn bwd", timeit(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, hd, a.W), a.iters, nbuf), None,
+            8.0 * M * D * 2)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
