@@ -555,7 +555,10 @@ int gemm_bf16(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int
   FAVIT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tcgen05: M,N,K must be positive (got %d,%d,%d)", M, N, K);
   FAVIT_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "gemm_tcgen05: operands must be 16-byte aligned");
   FAVIT_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_tcgen05: leading dimensions must be multiples of 8 elements");
-  // the contiguous extent of each operand must itself be a multiple of 8 elements (TMA global dims)
+  // force_bn: 0 = auto (CTA-pair kernel for large shapes), 512 = CTA-pair kernel, 64/128/256 = this kernel
+  if ((force_bn == 0 || force_bn == 512) && gemm_bf16_2cta_applicable(M, N, K, epi, lda, ldb))
+    return gemm_bf16_2cta(A, a_mn, lda, B, b_mn, ldb, M, N, K, epi, force_splits, st);
+  if (force_bn == 512) force_bn = 0;
   const int sms = num_sms();
   const int m_tiles = ceil_div(M, BM);
   const int k_blocks = ceil_div(K, BK);

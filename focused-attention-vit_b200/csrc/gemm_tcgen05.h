@@ -29,6 +29,11 @@ struct Epilogue {
 int gemm_bf16(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
               const Epilogue& epi, int force_bn, int force_splits, cudaStream_t st);
 
+// CTA-pair kernel (gemm_tcgen05_2cta.cu): 256 x 256 tiles, TMA-store epilogue.
+bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t lda, int64_t ldb);
+int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
+                   const Epilogue& epi, int force_splits, cudaStream_t st);
+
 }  // namespace tc
 
 // fp32 SIMT GEMM (parity path): C[m,n] = sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]

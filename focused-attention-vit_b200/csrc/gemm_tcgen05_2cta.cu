@@ -1,0 +1,486 @@
+// bf16 GEMM, CTA-pair version: tcgen05.mma.cta_group::2 (M = 256 per pair), operands by TMA, epilogue through
+// shared-memory staging and TMA stores.  Same contract and reference spans as gemm_tcgen05.cu (mhla.py:100,158 and
+// the MLP of vit.py:107-139, forward / dgrad / wgrad); this is the kernel the large shapes of the training step use.
+//
+// Why a second kernel: with one CTA per tile, a 128 x 256 tile reads 12 KiB of operands from shared memory per 128
+// tensor-pipe cycles (96 of the 128 B/clk an SM has) and the per-row global accesses of its epilogue compete for what
+// is left.  A CTA pair splits B: each SM stages 128 x 64 of A and only 128 x 64 of B per k-block (64 B/clk), the pair
+// issues one M = 256 instruction, and the freed shared-memory bandwidth pays for an epilogue that goes
+//   TMEM -> registers (bias / GELU / GELU') -> swizzled shared memory -> cp.async.bulk.tensor store
+// so that global traffic is whole 128-byte lines issued by the TMA unit (and `cp.reduce.async.bulk ... add` replaces
+// per-element atomics for split-K weight gradients).  The GELU' operand is prefetched by TMA loads as well.
+//
+// Cluster of 2 CTAs = one 256 x 256 output tile at a time (persistent, 74 clusters).  Per CTA, 384 threads:
+//   warp 0: TMA producer (its own 128 rows of A and 128 rows of B; bytes are signalled on the LEADER's full barrier)
+//   warp 1: MMA issuer (leader CTA only); tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
+//   warp 2: TMEM allocator (cta_group::2, 512 columns = two 256-column fp32 accumulators)
+//   warps 4-11: epilogue; warp w owns TMEM lanes 32*(w%4).. (32 rows) and 128 of the 256 columns.
+#include <mutex>
+
+#include "favit_common.cuh"
+#include "gemm_epilogue.cuh"
+#include "gemm_tcgen05.h"
+#include "tcgen05_ptx.cuh"
+
+namespace favit {
+namespace tc {
+namespace {
+
+using namespace ptx;
+
+constexpr int BMC = 128;   // rows per CTA
+constexpr int BM2 = 256;   // rows per cluster tile
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kABytes = BMC * BK * 2;        // 16 KiB
+constexpr uint32_t kBBytes = (BN / 2) * BK * 2;   // 16 KiB: each CTA stages half of B
+constexpr uint32_t kStage = kABytes + kBBytes;
+constexpr uint32_t kSlabBytes = 64 * 128;
+constexpr uint32_t kUnit = 32 * 128;              // one staging unit: 32 rows x 128 bytes
+
+template <bool AUX> constexpr int stages() { return AUX ? 4 : 5; }
+template <bool AUX> constexpr int out_bufs() { return AUX ? 1 : 2; }
+template <bool AUX> constexpr uint32_t smem_bytes() {
+  return stages<AUX>() * kStage + kEpiWarps * out_bufs<AUX>() * kUnit + (AUX ? kEpiWarps * 2 * kUnit : 0) + 1024 + 512;
+}
+
+struct K2Params {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  int a_mn, b_mn;
+  const float* bias;
+  int act;       // FAVIT_EPI_NONE / GELU (writes the pre-activation through tmC2) / DGELU_MUL (reads tmAux)
+  int c_fp32;    // C element type: 1 = fp32 (box 32 x 32), 0 = bf16 (box 64 x 32)
+  int reduce;    // accumulate into C with TMA reduce-add (split-K or accumulate)
+};
+
+// this lane's 32-column slice -> its row of a swizzled staging unit (bf16: 4 x 16-byte chunks at chunk offset `c4`)
+__device__ __forceinline__ void stage_bf16(uint8_t* unit, int lane, int c4, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(unit + lane * 128 + (((c4 + j) ^ (lane & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32(uint8_t* unit, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(unit + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void unstage_bf16(const uint8_t* unit, int lane, int c4, float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(unit + lane * 128 + (((c4 + j) ^ (lane & 7)) << 4));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      x[8 * j + 2 * t] = __uint_as_float(w[t] << 16);
+      x[8 * j + 2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u);
+    }
+  }
+}
+
+template <bool AUX>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                              const __grid_constant__ CUtensorMap tmAux, const K2Params p) {
+  constexpr int S = stages<AUX>();
+  constexpr int NOUT = out_bufs<AUX>();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);           // generic pointer to the aligned base
+  const uint32_t out_base = smem_base + S * kStage;
+  const uint32_t aux_base = out_base + kEpiWarps * NOUT * kUnit;
+  const uint32_t bar_base = aux_base + (AUX ? kEpiWarps * 2 * kUnit : 0);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  auto aux_bar = [&](int w) { return bar_base + 8u * (2 * S + 4 + w); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + kEpiWarps);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    if (p.act == FAVIT_EPI_GELU) prefetch_tmap(&tmC2);
+    if (AUX) prefetch_tmap(&tmAux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * kEpiWarps);  // every epilogue warp of both CTAs
+    }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(aux_bar(w), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // barriers of both CTAs are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < total_units; u += num_clusters) {
+        const int tile = u / p.splits, split = u % p.splits;
+        const int m0 = (tile / p.n_tiles) * BM2 + (int)rank * BMC;
+        const int n0 = (tile % p.n_tiles) * BN + (int)rank * (BN / 2);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * kStage;
+          const uint32_t sb = sa + kABytes;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * kStage);  // both CTAs' loads land on this barrier
+          const int k0 = kb * BK;
+          if (p.a_mn) {
+            tma_load_2d_pair(sa, &tmA, full_bar(stage), m0, k0);
+            tma_load_2d_pair(sa + kSlabBytes, &tmA, full_bar(stage), m0 + 64, k0);
+          } else {
+            tma_load_2d_pair(sa, &tmA, full_bar(stage), k0, m0);
+          }
+          if (p.b_mn) {
+            tma_load_2d_pair(sb, &tmB, full_bar(stage), n0, k0);
+            tma_load_2d_pair(sb + kSlabBytes, &tmB, full_bar(stage), n0 + 64, k0);
+          } else {
+            tma_load_2d_pair(sb, &tmB, full_bar(stage), k0, n0);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc(BM2, BN, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = cluster_id; u < total_units; u += num_clusters) {
+        const int split = u % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStage;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 2048u, kSlabBytes, 1024u)
+                                       : make_smem_desc(sa + k * 32u, 16u, 1024u);
+            const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048u, kSlabBytes, 1024u)
+                                       : make_smem_desc(sb + k * 32u, 16u, 1024u);
+            umma_bf16_pair(tmem_c, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp - 4;
+    const int wq = warp & 3;      // TMEM lane quarter
+    const int chalf = ew >> 2;    // which 128 of the tile's 256 columns
+    uint8_t* outbuf = smem_gen + (out_base - smem_base) + ew * NOUT * kUnit;
+    const uint32_t outbuf_u32 = out_base + ew * NOUT * kUnit;
+    uint8_t* auxbuf = smem_gen + (aux_base - smem_base) + ew * 2 * kUnit;
+    const uint32_t auxbuf_u32 = aux_base + ew * 2 * kUnit;
+    const bool b_vec = p.bias ? (((uintptr_t)p.bias) % 16 == 0) : false;
+    int acc = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
+    int obuf = 0;  // next staging buffer (round robin)
+    for (int u = cluster_id; u < total_units; u += num_clusters) {
+      const int tile = u / p.splits;
+      const int row0 = (tile / p.n_tiles) * BM2 + (int)rank * BMC + wq * 32;
+      const int col0 = (tile % p.n_tiles) * BN + chalf * 128;
+      if (AUX && lane == 0) {  // GELU' operand of this warp's 32 x 128 patch, prefetched while the MMAs still run
+        mbar_expect_tx(aux_bar(ew), 2 * kUnit);
+        tma_load_2d(auxbuf_u32, &tmAux, aux_bar(ew), col0, row0);
+        tma_load_2d(auxbuf_u32 + kUnit, &tmAux, aux_bar(ew), col0 + 64, row0);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (AUX) {
+        mbar_wait(aux_bar(ew), aux_phase);
+        aux_phase ^= 1u;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + chalf * 128);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int col = col0 + c * 32;
+        if (p.bias) {
+          if (b_vec && col + 32 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+          }
+        }
+        if (p.c_fp32) {
+          // one staging unit per 32 columns
+          uint8_t* ub = outbuf + obuf * kUnit;
+          if (lane == 0) tma_store_wait_read<NOUT - 1>();
+          __syncwarp();
+          stage_f32(ub, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col < p.N) {
+            if (p.reduce) tma_reduce_add_2d(&tmC, outbuf_u32 + obuf * kUnit, col, row0);
+            else tma_store_2d(&tmC, outbuf_u32 + obuf * kUnit, col, row0);
+          }
+          if (lane == 0) tma_store_commit();
+          obuf = (obuf + 1) % NOUT;
+        } else if (p.act == FAVIT_EPI_GELU) {
+          // two bf16 outputs per 64-column unit: buffer 0 = pre-activation, buffer 1 = activation
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          stage_bf16(outbuf, lane, (c & 1) * 4, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          stage_bf16(outbuf + (NOUT - 1) * kUnit, lane, (c & 1) * 4, v);
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int ucol = col - 32;
+            if (lane == 0 && ucol < p.N) {
+              tma_store_2d(&tmC2, outbuf_u32, ucol, row0);
+              tma_store_2d(&tmC, outbuf_u32 + (NOUT - 1) * kUnit, ucol, row0);
+            }
+            if (lane == 0) tma_store_commit();
+          }
+        } else {
+          if (AUX) {  // v *= gelu'(pre-activation)
+            float x[32];
+            unstage_bf16(auxbuf + (c >> 1) * kUnit, lane, (c & 1) * 4, x);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= dgelu_fast(x[i]);
+          }
+          uint8_t* ub = outbuf + obuf * kUnit;
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read<NOUT - 1>();
+            __syncwarp();
+          }
+          stage_bf16(ub, lane, (c & 1) * 4, v);
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int ucol = col - 32;
+            if (lane == 0 && ucol < p.N) tma_store_2d(&tmC, outbuf_u32 + obuf * kUnit, ucol, row0);
+            if (lane == 0) tma_store_commit();
+            obuf = (obuf + 1) % NOUT;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();  // the stores read this CTA's shared memory: finish before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // the peer may still be signalling our barriers / reading our operands until here
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D tensor, `inner` contiguous elements of `esize` bytes, rows `ld` elements apart; box = box_inner x box_rows
+int make_tmap(CUtensorMap* tm, const void* ptr, int esize, uint64_t inner, uint64_t outer, int64_t ld,
+              uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("gemm_tcgen05_2cta: cuTensorMapEncodeTiled is not available from the driver");
+    return FAVIT_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tcgen05_2cta: cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p inner=%llu outer=%llu ld=%lld)",
+              (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer, (long long)ld);
+    return FAVIT_ERR_CUDA;
+  }
+  return FAVIT_OK;
+}
+
+template <bool AUX>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tc2,
+           const CUtensorMap& taux, const K2Params& kp, int clusters, cudaStream_t st) {
+  static bool configured = false;
+  constexpr uint32_t smem = smem_bytes<AUX>();
+  if (!configured) {
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<AUX>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FAVIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<AUX>, ta, tb, tc_, tc2, taux, kp));
+  count_launch();
+  return FAVIT_OK;
+}
+
+}  // namespace
+
+bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t lda, int64_t ldb) {
+  if (M < 2048 || N < 256 || K < 64) return false;                 // small problems: the 1-CTA kernel's narrower tiles
+  if (e.residual != nullptr) return false;                          // fp32 residual epilogue stays on the 1-CTA kernel
+  const int es = e.c_dtype == FAVIT_BF16 ? 2 : 4;
+  if (((uintptr_t)e.c % 16) || ((e.ldc * es) % 16)) return false;   // TMA store pitch
+  if (e.act == FAVIT_EPI_GELU && (e.c_dtype != FAVIT_BF16 || !e.aux_out || ((uintptr_t)e.aux_out % 16) || ((e.ldaux * 2) % 16)))
+    return false;
+  if (e.act == FAVIT_EPI_DGELU_MUL && (e.c_dtype != FAVIT_BF16 || !e.aux || ((uintptr_t)e.aux % 16) || ((e.ldaux * 2) % 16)))
+    return false;
+  if (e.accumulate && e.c_dtype != FAVIT_F32) return false;
+  return true;
+}
+
+int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
+                   const Epilogue& epi, int force_splits, cudaStream_t st) {
+  const int sms = num_sms();
+  const int clusters_max = sms / 2;
+  const int m_tiles = ceil_div(M, BM2), n_tiles = ceil_div(N, BN), k_blocks = ceil_div(K, BK);
+  const int64_t tiles = (int64_t)m_tiles * n_tiles;
+  const bool can_split = epi.c_dtype == FAVIT_F32 && epi.bias == nullptr && epi.act == FAVIT_EPI_NONE && epi.split_ok;
+  int splits = 1;
+  if (force_splits > 0) {
+    splits = force_splits;
+  } else if (can_split) {
+    double best = 1e30;
+    const int smax = min(32, max(1, k_blocks / 4));
+    for (int sp = 1; sp <= smax; ++sp) {
+      const int kps = ceil_div(k_blocks, sp);
+      const int sp_eff = ceil_div(k_blocks, kps);
+      const double waves = (double)ceil_div64(tiles * sp_eff, clusters_max);
+      const double cost = waves * (kps * 512.0 + 2500.0);
+      if (cost < best) { best = cost; splits = sp_eff; }
+    }
+  }
+  FAVIT_CHECK_ARG(splits == 1 || can_split, "gemm_tcgen05_2cta: split-K needs a plain fp32 accumulate epilogue");
+  const int kb_per_split = ceil_div(k_blocks, splits);
+  splits = ceil_div(k_blocks, kb_per_split);
+
+  CUtensorMap ta, tb, tcm, tc2, taux;
+  int rc;
+  rc = a_mn ? make_tmap(&ta, A, 2, (uint64_t)M, (uint64_t)K, lda, 64, 64) : make_tmap(&ta, A, 2, (uint64_t)K, (uint64_t)M, lda, 64, BMC);
+  if (rc) return rc;
+  rc = b_mn ? make_tmap(&tb, B, 2, (uint64_t)N, (uint64_t)K, ldb, 64, 64) : make_tmap(&tb, B, 2, (uint64_t)K, (uint64_t)N, ldb, 64, BN / 2);
+  if (rc) return rc;
+  const bool c_fp32 = epi.c_dtype == FAVIT_F32;
+  rc = make_tmap(&tcm, epi.c, c_fp32 ? 4 : 2, (uint64_t)N, (uint64_t)M, epi.ldc, c_fp32 ? 32 : 64, 32);
+  if (rc) return rc;
+  tc2 = tcm;
+  taux = tcm;
+  if (epi.act == FAVIT_EPI_GELU) {
+    rc = make_tmap(&tc2, epi.aux_out, 2, (uint64_t)N, (uint64_t)M, epi.ldaux, 64, 32);
+    if (rc) return rc;
+  }
+  const bool aux = epi.act == FAVIT_EPI_DGELU_MUL;
+  if (aux) {
+    rc = make_tmap(&taux, epi.aux, 2, (uint64_t)N, (uint64_t)M, epi.ldaux, 64, 32);
+    if (rc) return rc;
+  }
+  K2Params kp;
+  kp.M = M; kp.N = N; kp.K = K;
+  kp.m_tiles = m_tiles; kp.n_tiles = n_tiles; kp.k_blocks = k_blocks;
+  kp.splits = splits; kp.kb_per_split = kb_per_split;
+  kp.a_mn = a_mn; kp.b_mn = b_mn;
+  kp.bias = epi.bias;
+  kp.act = epi.act;
+  kp.c_fp32 = c_fp32 ? 1 : 0;
+  kp.reduce = (splits > 1 || epi.accumulate) ? 1 : 0;
+  const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
+  return aux ? launch<true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
+             : launch<false>(ta, tb, tcm, tc2, taux, kp, clusters, st);
+}
+
+}  // namespace tc
+}  // namespace favit

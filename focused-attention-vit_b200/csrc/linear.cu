@@ -169,6 +169,6 @@ extern "C" int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const v
   FAVIT_CHECK_ARG(a && b && c, "gemm_bf16_raw: null pointer");
   tc::Epilogue e;
   e.c = c; e.ldc = ldc; e.c_dtype = c_dtype;
-  e.split_ok = (splits > 1) ? 1 : 0;
+  e.split_ok = (splits != 1) ? 1 : 0;
   return tc::gemm_bf16(a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, M, N, K, e, bn, splits, (cudaStream_t)stream);
 }

@@ -68,9 +68,9 @@ def test_linear_fwd_bwd(dtype, M, K, N):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-def test_linear_epilogues(dtype):
+@pytest.mark.parametrize("M,K,N", [(520, 128, 392), (4200, 256, 648)], ids=["small", "cta_pair"])
+def test_linear_epilogues(dtype, M, K, N):
     from favit_b200 import ops
-    M, K, N = 520, 128, 392
     x = torch.randn(M, K, device="cuda").to(dtype)
     w = (torch.randn(N, K, device="cuda") * 0.1).to(dtype)
     b = torch.randn(N, device="cuda")
