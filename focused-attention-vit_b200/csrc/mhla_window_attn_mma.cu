@@ -160,6 +160,31 @@ struct KeySlots {
     return (j == r.tgt) ? r.pad : 0;  // an edge row outside the band: only the duplicated index reaches it
   }
 };
+// Per-query view of a key-slot list: slots [s_lo, s_hi] are the band (multiplicity 1), slot `ts` is the duplicated edge
+// key; log2 of the multiplicities is precomputed so that the per-element work is two compares and a select.
+struct RowSlots {
+  int s_lo, s_span, ts;
+  float lb_in, lb_out;   // log2(1 + pad) when the edge key lies inside the band, log2(pad) (or -inf) when outside
+  __device__ __forceinline__ float bias(int slot) const {
+    const bool in_band = (unsigned)(slot - s_lo) <= (unsigned)s_span;
+    const bool edge = slot == ts;
+    return in_band ? (edge ? lb_in : 0.f) : (edge ? lb_out : -CUDART_INF_F);
+  }
+};
+__device__ __forceinline__ RowSlots row_slots(const KeySlots& k, int i, int N, int W) {
+  const WindowRow r = window_row(i, N, W);
+  RowSlots o;
+  o.s_lo = r.s - k.lo;
+  o.s_span = r.e - 1 - r.s;
+  const int hi = k.lo + k.nband - 1;
+  if (r.tgt >= k.lo && r.tgt <= hi) o.ts = r.tgt - k.lo;
+  else o.ts = (r.tgt == N - 1) ? (k.exA ? k.nband : -1) : (k.exB ? k.nband + 1 : -1);
+  if (r.pad == 0) o.ts = -1;
+  o.lb_in = log2f((float)(1 + r.pad));
+  o.lb_out = r.pad > 0 ? log2f((float)r.pad) : -CUDART_INF_F;
+  return o;
+}
+
 __device__ __forceinline__ KeySlots key_slots(int i0, int N, int W) {
   const int h = W >> 1;
   KeySlots k;
@@ -249,15 +274,14 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_fwd_kernel(const __nv_bf
   scores<HD, NT>(sQ, sK, lane, s);
 
   const int r0 = lane >> 2;
-  const WindowRow w0 = window_row(min(i0 + r0, N - 1), N, sh.W), w1 = window_row(min(i0 + r0 + 8, N - 1), N, sh.W);
+  const RowSlots w0 = row_slots(ks, min(i0 + r0, N - 1), N, sh.W), w1 = row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
   float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int slot = nt * 8 + (lane & 3) * 2 + (e & 1);
-      const int m = ks.mult(e < 2 ? w0 : w1, slot);
-      const float val = (m > 0) ? fmaf(s[nt][e], sh.scale_log2, (m > 1) ? log2f((float)m) : 0.f) : -CUDART_INF_F;
+      const float val = fmaf(s[nt][e], sh.scale_log2, (e < 2 ? w0 : w1).bias(slot));  // -inf outside the window
       s[nt][e] = val;
       if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
     }
@@ -349,22 +373,17 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dq_kernel(
 
   const int r0 = lane >> 2;
   const bool ok0 = i0 + r0 < N, ok1 = i0 + r0 + 8 < N;
-  const WindowRow w0 = window_row(min(i0 + r0, N - 1), N, sh.W), w1 = window_row(min(i0 + r0 + 8, N - 1), N, sh.W);
+  const RowSlots w0 = row_slots(ks, min(i0 + r0, N - 1), N, sh.W), w1 = row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
   const float* l = lse + ((int64_t)b * sh.H + h) * N;
-  const float L0 = ok0 ? l[i0 + r0] * kLog2e : 0.f, L1 = ok1 ? l[i0 + r0 + 8] * kLog2e : 0.f;
+  // rows past the end of the sequence get L = +inf, i.e. P = 0
+  const float L0 = ok0 ? l[i0 + r0] * kLog2e : CUDART_INF_F, L1 = ok1 ? l[i0 + r0 + 8] * kLog2e : CUDART_INF_F;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int slot = nt * 8 + (lane & 3) * 2 + (e & 1);
-      const int m = ks.mult(e < 2 ? w0 : w1, slot);
-      const bool ok = (e < 2) ? ok0 : ok1;
-      float ds = 0.f;
-      if (m > 0 && ok) {
-        const float p = exp2f(fmaf(s[nt][e], sh.scale_log2, (m > 1) ? log2f((float)m) : 0.f) - (e < 2 ? L0 : L1));
-        ds = p * (dp[nt][e] - (e < 2 ? d0 : d1));
-      }
-      s[nt][e] = ds;
+      const float p = exp2f(fmaf(s[nt][e], sh.scale_log2, (e < 2 ? w0 : w1).bias(slot)) - (e < 2 ? L0 : L1));
+      s[nt][e] = p * (dp[nt][e] - (e < 2 ? d0 : d1));
     }
   float acc[HD / 8][4];
 #pragma unroll
@@ -445,7 +464,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dkv_kernel(
   });
   for (int s = lane; s < NQ; s += 32) {
     const int i = qs.query(s);
-    sL[s] = i >= 0 ? lse[((int64_t)b * sh.H + h) * N + i] * kLog2e : 0.f;
+    sL[s] = i >= 0 ? lse[((int64_t)b * sh.H + h) * N + i] * kLog2e : CUDART_INF_F;
     sD[s] = i >= 0 ? delta[((int64_t)b * sh.H + h) * N + i] : 0.f;
   }
   cp_async_wait_all();
@@ -464,19 +483,20 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dkv_kernel(
       const int slot = nt * 8 + (lane & 3) * 2 + c;
       const int i = qs.query(slot);
       const WindowRow w = window_row(max(i, 0), N, sh.W);
+      // unused slots carry L = +inf (P = 0); keys past the end of the sequence are never stored
       const float L = sL[slot], dl = sD[slot];
+      const float lb_in = log2f((float)(1 + w.pad));
+      const float lb_out = w.pad > 0 ? log2f((float)w.pad) : -CUDART_INF_F;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int e = half * 2 + c;
         const int j = half ? jb : ja;
-        const int m = (i >= 0 && j < N) ? window_mult(w, j) : 0;
-        float p = 0.f, ds = 0.f;
-        if (m > 0) {
-          p = exp2f(fmaf(s[nt][e], sh.scale_log2, (m > 1) ? log2f((float)m) : 0.f) - L);
-          ds = p * (dp[nt][e] - dl);
-        }
+        const bool in_band = (unsigned)(j - w.s) < (unsigned)(w.e - w.s);
+        const bool edge = j == w.tgt;
+        const float bias = in_band ? (edge ? lb_in : 0.f) : (edge ? lb_out : -CUDART_INF_F);
+        const float p = exp2f(fmaf(s[nt][e], sh.scale_log2, bias) - L);
         s[nt][e] = p;
-        dp[nt][e] = ds;
+        dp[nt][e] = p * (dp[nt][e] - dl);
       }
     }
   __syncwarp();  // K / V tiles are dead from here on: reuse them as staging
