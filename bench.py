@@ -229,7 +229,7 @@ def run_favit(args, wl, rank, world, local_rank):
     model = build_model(wl, device)
     if wl["kind"] == "sppp":
         model.validate_slots = False          # synthetic maps are validated once, below, not once per step
-    step = TrainStep(model, process_group=None)
+    step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph)
     # distinct batches so that no step can reuse a cached input; seed differs per rank
     nb = 2
     batches = [make_batch(wl, B, seed=1234 + rank * 100 + i, device=device) for i in range(nb)]
@@ -242,19 +242,28 @@ def run_favit(args, wl, rank, world, local_rank):
         x, y, maps = batches[i % nb]
         return step(x, y, maps)
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 5 if args.cuda_graph else 0)):   # graph mode: 3 eager steps, capture, 1 replay
         dev_step(i)
     torch.cuda.synchronize(device)
 
     # ---- device-resident throughput (`value`) with per-launch event timing for the roofline ----
     sampler = ClockSampler(local_rank)
-    L.PROFILE = []
+    L.PROFILE = None if args.cuda_graph else []   # per-launch events cannot be recorded inside a replayed graph
     launches0 = L.launch_count()
     sampler.start()
     ms_total = timed_steps(dev_step, args.steps, dist_on, device)
     clocks = sampler.stop()
     launches = L.launch_count() - launches0
-    prof, L.PROFILE = L.PROFILE, None
+    prof, L.PROFILE = (L.PROFILE or []), None
+    if args.cuda_graph:
+        # launch count and per-family timing come from one eager step of the same model (outside the timed region)
+        L.PROFILE = []
+        l0 = L.launch_count()
+        step._eager(*batches[0])
+        torch.cuda.synchronize(device)
+        launches = (L.launch_count() - l0) * args.steps
+        prof, L.PROFILE = L.PROFILE, None
+        prof = prof * args.steps
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
 
@@ -309,7 +318,7 @@ def run_favit(args, wl, rank, world, local_rank):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": world * B, "per_gpu_batch": B, "img": wl["img"],
                    "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"], "window": wl["W"],
-                   "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "adamw(fused) in step",
+                   "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "adamw(fused) in step", "cuda_graph": bool(args.cuda_graph),
                    "l2": "working set >> L2 every step (inputs %.0f MB, activations several GB); no flush needed"
                          % (h2d / 1e6)},
         "clocks": clocks,
@@ -340,6 +349,10 @@ def main():
     ap.add_argument("--workload", default="vitb16_mhla_224", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true",
+                    help="capture the training step in a CUDA graph (default)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    ap.set_defaults(cuda_graph=None)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "favit":
         args.warmup = 3
@@ -347,6 +360,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    if args.cuda_graph is None:
+        args.cuda_graph = True
     if args.impl == "reference":
         run_reference_arm(args, wl, rank)
         return

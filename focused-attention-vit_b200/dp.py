@@ -56,6 +56,7 @@ class GradAllReducer:
         self._pending = list(self._size)
         self._works = []
         self._handles = []
+        self.overlap = True
         if self.enabled:
             # gloo has no AVG: sum and scale afterwards
             self._avg = dist.ReduceOp.AVG if dist.get_backend(process_group) == "nccl" else None
@@ -70,6 +71,8 @@ class GradAllReducer:
         self._works = []
 
     def _hook(self, p: torch.nn.Parameter) -> None:
+        if not self.overlap:       # deferred mode (backward replayed from a CUDA graph): finish() reduces every bucket
+            return
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -86,7 +89,7 @@ class GradAllReducer:
         if not self.enabled:
             return
         for bi, left in enumerate(self._pending):
-            if left != 0:
+            if left != 0 or not self.overlap:
                 op = self._avg if self._avg is not None else dist.ReduceOp.SUM
                 self._works.append((dist.all_reduce(self.buckets[bi], op=op, group=self.group, async_op=True), bi))
                 self._pending[bi] = 0

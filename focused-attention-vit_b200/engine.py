@@ -16,29 +16,83 @@ from .dp import GradAllReducer
 
 
 class TrainStep:
+    """cuda_graph=True captures the whole step (forward, loss, backward with the overlapped all-reduce, AdamW) into one
+    CUDA graph after three eager warm-up steps and replays it afterwards: the launch-bound small workloads (SPPP +
+    ViT-S: ~1300 launches of 5-10 us each) then run at GPU speed instead of Python speed.  Inputs are copied into the
+    graph's static buffers; shapes must not change between calls."""
+
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.05,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 32.0,
-                 optimizer: bool = True):
+                 optimizer: bool = True, cuda_graph: bool = False):
         self.model = model
         self.autocast_dtype = autocast_dtype
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group)
         # lr / weight decay: the reference's defaults (main.py:129-132)
-        self.opt = (torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True)
+        self.opt = (torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
+                                      capturable=cuda_graph)
                     if optimizer else None)
+        self.cuda_graph = cuda_graph
+        self._graph = None
+        self._graph_opt = None
+        self._static = None
+        self._static_loss = None
+        self._calls = 0
 
-    def __call__(self, images: torch.Tensor, labels: torch.Tensor,
-                 segmentation_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Device tensors in, detached scalar loss (device tensor) out."""
+    def _fwd_bwd(self, images, labels, segmentation_maps):
         self.reducer.zero_grad()
         with torch.autocast("cuda", dtype=self.autocast_dtype or torch.bfloat16,
                             enabled=self.autocast_dtype is not None):
             logits = self.model(images) if segmentation_maps is None else self.model(images, segmentation_maps)
         loss = F.cross_entropy(logits.float(), labels)
         loss.backward()
+        return loss.detach()
+
+    def _eager(self, images, labels, segmentation_maps):
+        loss = self._fwd_bwd(images, labels, segmentation_maps)
         self.reducer.finish()
         if self.opt is not None:
             self.opt.step()
-        return loss.detach()
+        return loss
+
+    def _capture(self, images, labels, segmentation_maps):
+        """Single GPU: one graph for the whole step.  Data parallel: graph A = zero_grad + forward + backward, then the
+        bucketed all-reduce is issued eagerly (NCCL collectives are kept out of stream capture), then graph B = AdamW.
+        The un-overlapped all-reduce costs ~1 ms of a ~37 ms ViT-B step at 8 GPUs; the eager path (cuda_graph=False)
+        keeps the overlap instead."""
+        self._static = [images.clone(), labels.clone(), None if segmentation_maps is None else segmentation_maps.clone()]
+        self._graph = torch.cuda.CUDAGraph()
+        if not self.reducer.enabled:
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self._eager(*self._static)
+            return
+        self.reducer.overlap = False
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._fwd_bwd(*self._static)
+        if self.opt is not None:
+            self._graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
+                self.opt.step()
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor,
+                 segmentation_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device tensors in, detached scalar loss (device tensor) out."""
+        if not self.cuda_graph:
+            return self._eager(images, labels, segmentation_maps)
+        self._calls += 1
+        if self._calls <= 3:                      # eager warm-up: lazy initialisation must not be captured
+            return self._eager(images, labels, segmentation_maps)
+        if self._graph is None:
+            torch.cuda.synchronize()
+            self._capture(images, labels, segmentation_maps)
+        for dst, src in zip(self._static, (images, labels, segmentation_maps)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        if self.reducer.enabled:
+            self.reducer.finish()                 # every bucket: hooks are off in deferred mode
+            if self._graph_opt is not None:
+                self._graph_opt.replay()
+        return self._static_loss
 
 
 class HostBatchFeeder:
