@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
                                                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                                                     int D) {
-  extern __shared__ float s_red[];          // [2][pairs][D] for the final dgamma/dbeta combine
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ dxsum, int M, int D) {
+  extern __shared__ float s_red[];          // [3][pairs][D] for the final dgamma / dbeta / dx-column-sum combine
   __shared__ float2 s_xchg[2][2][2];        // [parity][pair][half] = (sum g, sum g*xhat)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pair = warp >> 1, half = warp & 1, npairs = blockDim.x >> 6;
@@ -141,11 +141,11 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
   const int nvh = (nvec + 1) >> 1;           // float4 chunks per half
   const int cbase = half * nvh;
   const int cend = min(nvec, cbase + nvh);
-  float dg[NVH][4], db[NVH][4];
+  float dg[NVH][4], db[NVH][4], ds[NVH][4];   // ds: column sums of dx = the bias gradient of the linear that fed x
 #pragma unroll
   for (int i = 0; i < NVH; ++i)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
+    for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; ds[i][e] = 0.f; }
   const float invD = 1.f / (float)D;
   int parity = 0;
   for (int row = blockIdx.x * npairs + pair; row < M; row += gridDim.x * npairs, parity ^= 1) {
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
         for (int e = 0; e < 4; ++e) {
           o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
           if (dres) o[e] += rr[i][e];
+          ds[i][e] += o[e];
         }
         store4(dx + (int64_t)row * D + 4 * c, o);
         if (dx_bf16) store4(dx_bf16 + (int64_t)row * D + 4 * c, o);
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
   if (dgamma == nullptr) return;
   float* sg = s_red;
   float* sb = s_red + (size_t)npairs * D;
+  float* ss = s_red + (size_t)2 * npairs * D;
 #pragma unroll
   for (int i = 0; i < NVH; ++i) {
     const int c = cbase + lane + 32 * i;
@@ -215,18 +217,21 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
       for (int e = 0; e < 4; ++e) {
         sg[pair * D + 4 * c + e] = dg[i][e];
         sb[pair * D + 4 * c + e] = db[i][e];
+        ss[pair * D + 4 * c + e] = ds[i][e];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, d = 0.f;
     for (int w = 0; w < npairs; ++w) {
       a += sg[w * D + c];
       b += sb[w * D + c];
+      d += ss[w * D + c];
     }
     atomicAdd(dgamma + c, a);
     atomicAdd(dbeta + c, b);
+    if (dxsum) atomicAdd(dxsum + c, d);
   }
 }
 
@@ -276,10 +281,11 @@ extern "C" int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const voi
 
 extern "C" int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const void* x, favit_dtype x_dtype,
                                    const float* mean, const float* rstd, const float* gamma, const float* dres,
-                                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, int M, int D,
+                                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D,
                                    favit_stream stream) {
   FAVIT_CHECK_ARG(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
   FAVIT_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta come together");
+  FAVIT_CHECK_ARG(dxsum == nullptr || dgamma != nullptr, "layernorm_bwd: dxsum needs dgamma / dbeta");
   FAVIT_CHECK_ARG(M > 0 && D > 0, "layernorm_bwd: M, D must be positive");
   if (D % 4 != 0 || D > 128 * kMaxVec) {
     set_error("layernorm_bwd: D=%d unsupported (needs D %% 4 == 0 and D <= %d)", D, 128 * kMaxVec);
@@ -287,11 +293,11 @@ extern "C" int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const v
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int pairs = 2;                                          // rows in flight per CTA (2 warps each)
-  const size_t smem = (size_t)2 * pairs * D * sizeof(float);   // <= 16 KiB
+  const size_t smem = (size_t)3 * pairs * D * sizeof(float);   // <= 24 KiB
   const unsigned blocks = (unsigned)max(1, min(ceil_div(M, pairs), 6 * num_sms()));
 #define LN_BWD_NV(TX, TDY, NVH)                                                                                  \
   ln_bwd_kernel<TX, TDY, NVH><<<blocks, pairs * 64, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
-                                                                dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, D)
+                                                                dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, M, D)
 #define LN_BWD(TX, TDY)                           \
   do {                                            \
     if (D <= 256) LN_BWD_NV(TX, TDY, 1);          \

@@ -25,12 +25,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, f
   if (c0 < N) {
     if (vec) {
       int r = r0 + warp;
-      for (; r + 24 < r1; r += 32) {
-        float f[4][8];
+      for (; r + 56 < r1; r += 64) {  // 8 independent 16-byte loads in flight per thread
+        float f[8][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load8(dy + (int64_t)(r + 8 * u) * ld + c0, f[u]);
+        for (int u = 0; u < 8; ++u) load8(dy + (int64_t)(r + 8 * u) * ld + c0, f[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] += f[u][e];
       }
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, f
 template <typename T>
 int launch_colsum(const void* dy, float* db, int M, int N, int64_t ld, cudaStream_t st) {
   const int col_blocks = ceil_div(N, 256);
-  int row_blocks = max(1, min(ceil_div(M, 64), (4 * num_sms()) / col_blocks));
+  int row_blocks = max(1, min(ceil_div(M, 64), ceil_div(3 * num_sms(), col_blocks)));
   const int rows_per_cta = ceil_div(ceil_div(M, row_blocks), 8) * 8;
   row_blocks = ceil_div(M, rows_per_cta);
   colsum_kernel<T><<<dim3(col_blocks, row_blocks), 256, 0, st>>>((const T*)dy, db, M, N, ld, rows_per_cta);

@@ -72,27 +72,29 @@ def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, 
     hd = D // H
     bf = cd == torch.bfloat16
     g = g.contiguous()
-    if bf:
-        g_c = _GRAD_BF16.pop((g.data_ptr(), M, D), None)
-        if g_c is None:
-            g_c = g.to(cd)
+    # (operand copy in the compute dtype, column sums) of the incoming gradient, left behind by the LayerNorm backward of
+    # the block above; the column sums are this block's fc2 bias gradient
+    handed = _GRAD_BF16.pop((g.data_ptr(), M, D), None)
+    if handed is not None:
+        g_c, gsum = handed
     else:
-        g_c = g
-    dw2, db2 = raw.linear_wgrad(g_c, h)
+        g_c, gsum = (g.to(cd) if bf else g), None
+    dw2, db2 = raw.linear_wgrad(g_c, h, want_bias=gsum is None)
+    if gsum is not None:
+        db2 = gsum
     dhpre = raw.linear_dgrad(g_c, w2, hpre, cd)
     dw1, db1 = raw.linear_wgrad(dhpre, xn2)
     dxn2 = raw.linear_dgrad(dhpre, w1, None, cd)
-    g2, g2_b, dg2, dbt2 = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf)
+    g2, g2_b, dg2, dbt2, dbp = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf)   # dbp = column sums of g2
     g2_c = g2_b if bf else g2
-    dwp, dbp = raw.linear_wgrad(g2_c, o)
+    dwp, _ = raw.linear_wgrad(g2_c, o, want_bias=False)
     do = raw.linear_dgrad(g2_c, wproj, None, cd)
     dqkv = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window)
     dwq, dbq = raw.linear_wgrad(dqkv, xn)
     dxn = raw.linear_dgrad(dqkv, wqkv, None, cd)
-    g0, g0_b, dg1, dbt1 = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf)
-    if bf:
-        _GRAD_BF16.clear()                      # at most one hand-over is alive
-        _GRAD_BF16[(g0.data_ptr(), M, D)] = g0_b
+    g0, g0_b, dg1, dbt1, g0sum = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf)
+    _GRAD_BF16.clear()                          # at most one hand-over is alive
+    _GRAD_BF16[(g0.data_ptr(), M, D)] = (g0_b if bf else g0, g0sum)
     return [g0, dg1, dbt1, dwq, dbq, dwp, dbp, dg2, dbt2, dw1, db1, dw2, db2]
 
 

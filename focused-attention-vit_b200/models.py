@@ -160,8 +160,8 @@ class VisionTransformerMHLA(nn.Module):
         x = self.pos_drop(x + self.pos_embed)
         for block in self.blocks:
             x = block(x)
-        x = self.norm(x)
-        return x[:, 0]
+        # LayerNorm is per token and only the class token is used (vit_mhla.py:241-244): normalise that row alone
+        return self.norm(x[:, 0])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.head(self.forward_features(x))
@@ -291,8 +291,8 @@ class SPPPViTMHLA(nn.Module):
         x = self.pos_embed(x, self._calculate_superpixel_centroids(segmentation_maps))
         for block in self.blocks:
             x = block(x)
-        x = self.norm(x)
-        return self.head(x[:, 0])
+        # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone
+        return self.head(self.norm(x[:, 0]))
 
     def get_num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

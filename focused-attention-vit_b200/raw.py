@@ -75,18 +75,18 @@ def ln_fwd(x: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: 
 
 def ln_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
            want_bf16: bool):
-    """Returns (dx fp32, dx_bf16 or None, dgamma, dbeta)."""
+    """Returns (dx fp32, dx_bf16 or None, dgamma, dbeta, column sums of dx)."""
     M, D = x.shape
     dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
     dxb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    dg = torch.zeros((D,), dtype=torch.float32, device=x.device)
-    db = torch.zeros((D,), dtype=torch.float32, device=x.device)
+    acc = torch.zeros((3, D), dtype=torch.float32, device=x.device)
+    dg, db, dxs = acc[0], acc[1], acc[2]
     work = float(dy.numel() * dy.element_size() + x.numel() * x.element_size() + dx.numel() * 4 +
                  (dres.numel() * 4 if dres is not None else 0) + (dxb.numel() * 2 if want_bf16 else 0))
     rc = L.call("ln_bwd", work, L.lib().favit_layernorm_bwd, _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(mean),
-                _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb), _p(dg), _p(db), M, D, _s())
+                _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb), dg.data_ptr(), db.data_ptr(), dxs.data_ptr(), M, D, _s())
     L.check(rc, "favit_layernorm_bwd")
-    return dx, dxb, dg, db
+    return dx, dxb, dg.clone(), db.clone(), dxs.clone()
 
 
 def attn_fwd(qkv: Tensor, B: int, N: int, H: int, hd: int, window: int):

@@ -129,6 +129,8 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
  * favit_layernorm_bwd: dx[M,D] (fp32) = LN'(dy) + dres   (dres: fp32 gradient of the residual branch, may be NULL);
  *      dx_bf16 (may be NULL) receives a bf16 copy of dx (the operand of the next dgrad / wgrad GEMM);
  *      dgamma / dbeta [D] fp32 are ACCUMULATED into (zero them first); both NULL to skip.
+ *      dxsum [D] (may be NULL) accumulates the column sums of dx: dx is the output gradient of the linear layer
+ *      that fed this norm's residual input, so dxsum is that layer's bias gradient (no separate reduction pass).
  * ---------------------------------------------------------------------------------------------- */
 int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const void* delta, void* xsum, const float* gamma,
                         const float* beta, void* y, favit_dtype y_dtype, float* mean, float* rstd, int M, int D,
@@ -136,7 +138,8 @@ int favit_layernorm_fwd(const void* x, favit_dtype x_dtype, const void* delta, v
 
 int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const void* x, favit_dtype x_dtype,
                         const float* mean, const float* rstd, const float* gamma, const float* dres, float* dx,
-                        void* dx_bf16, float* dgamma, float* dbeta, int M, int D, favit_stream stream);
+                        void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D,
+                        favit_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SPPP patch -> superpixel assignment — replaces PatchToSuperpixelMapper.map_patches,

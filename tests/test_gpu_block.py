@@ -28,7 +28,9 @@ def test_layernorm_fwd_bwd(M, D, out_dtype):
     dy = torch.randn(M, D, device="cuda").to(out_dtype)
     dres = torch.randn(M, D, device="cuda")
     yr.backward(dy.double())
-    dx, dxb, dg, db = raw.ln_bwd(dy, x, mean, rstd, gamma, dres, True)
+    dx, dxb, dg, db, dxs = raw.ln_bwd(dy, x, mean, rstd, gamma, dres, True)
+    assert_close(dxs, (xr.grad + dres.double()).sum(dim=0), torch.float32, "dx column sums", factor=5.0,
+                 floor=1e-3 * float(dx.abs().max()) * M ** 0.5)
     assert_close(dx, xr.grad + dres.double(), torch.float32, "ln dx", factor=3.0)
     assert_close(dxb, xr.grad + dres.double(), torch.bfloat16, "ln dx bf16")
     assert_close(dg, gr.grad, torch.float32, "dgamma", factor=5.0)
