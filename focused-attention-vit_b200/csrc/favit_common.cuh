@@ -34,7 +34,7 @@ void count_launch(int n = 1);
 
 #define FAVIT_CHECK_LAUNCH()                                                                \
   do {                                                                                      \
-    cudaError_t _e = cudaPeekAtLastError();                                                 \
+    cudaError_t _e = cudaGetLastError(); /* clears it: one bad launch must not poison the rest */ \
     if (_e != cudaSuccess) {                                                                \
       ::favit::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
                          __FILE__, __LINE__);                                               \

@@ -123,9 +123,26 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
 }
 
 // Two warps per row (each owns one half of the columns, NVH float4 per lane), two rows in flight per 128-thread CTA,
-// persistent over rows.  Halving the per-thread column count keeps the dgamma/dbeta partials plus a whole row of
-// operands in registers without spilling, so every load of a row is in flight at once.  The two row sums are exchanged
-// between the warps of a pair through shared memory and a 64-thread named barrier (parity double-buffered).
+// persistent over rows.  The operands of a row (x, dy, dres) are staged through shared memory with cp.async, two rows
+// deep: an in-flight cp.async holds no registers, so a CTA keeps ~2 x 7.7 KB per row pair on the wire while it does
+// the reductions of the current row (ncu, round 1: the register-staged version sat at 20 % warp occupancy with 10
+// long-scoreboard stalls per issue and 3.6 TB/s).  Every thread reads back exactly the 16-byte slots it copied, so the
+// staging needs no barrier.  The two row sums are exchanged between the warps of a pair through shared memory and a
+// 64-thread named barrier (parity double-buffered).
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+template <typename T> __device__ __forceinline__ void cp_async_vec4(void* smem, const T* gmem);
+template <> __device__ __forceinline__ void cp_async_vec4<float>(void* smem, const float* gmem) { cp_async_16(smem, gmem); }
+template <> __device__ __forceinline__ void cp_async_vec4<__nv_bfloat16>(void* smem, const __nv_bfloat16* gmem) {
+  cp_async_8(smem, gmem);
+}
+
 template <typename TX, typename TDY, int NVH>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -133,41 +150,60 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ dxsum, int M, int D) {
-  extern __shared__ float s_red[];          // [3][pairs][D] for the final dgamma / dbeta / dx-column-sum combine
+  // staging: [stage 2][kind 3 = x, dy, dres][NVH][128 threads] 16-byte slots; reused as [3][pairs][D] floats at the end
+  extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ float2 s_xchg[2][2][2];        // [parity][pair][half] = (sum g, sum g*xhat)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = warp >> 1, half = warp & 1, npairs = blockDim.x >> 6;
   const int nvec = D >> 2;
   const int nvh = (nvec + 1) >> 1;           // float4 chunks per half
   const int cbase = half * nvh;
   const int cend = min(nvec, cbase + nvh);
+  auto slot = [&](int stage, int kind, int i) -> uint8_t* {
+    return s_dyn + ((size_t)((stage * 3 + kind) * NVH + i) * 128 + tid) * 16;
+  };
+  auto prefetch = [&](int row, int stage) {
+    if (row < M) {
+#pragma unroll
+      for (int i = 0; i < NVH; ++i) {
+        const int c = cbase + lane + 32 * i;
+        if (c < cend) {
+          cp_async_vec4<TX>(slot(stage, 0, i), x + (int64_t)row * D + 4 * c);
+          cp_async_vec4<TDY>(slot(stage, 1, i), dy + (int64_t)row * D + 4 * c);
+          if (dres) cp_async_16(slot(stage, 2, i), dres + (int64_t)row * D + 4 * c);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   float dg[NVH][4], db[NVH][4], ds[NVH][4];   // ds: column sums of dx = the bias gradient of the linear that fed x
 #pragma unroll
   for (int i = 0; i < NVH; ++i)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; ds[i][e] = 0.f; }
   const float invD = 1.f / (float)D;
+  const int stride = gridDim.x * npairs;
+  int row = blockIdx.x * npairs + pair;
   int parity = 0;
-  for (int row = blockIdx.x * npairs + pair; row < M; row += gridDim.x * npairs, parity ^= 1) {
-    const TX* xr = x + (int64_t)row * D;
-    const TDY* dyr = dy + (int64_t)row * D;
-    float xh[NVH][4], gy[NVH][4], rr[NVH][4];
-#pragma unroll
-    for (int i = 0; i < NVH; ++i) {
-      const int c = cbase + lane + 32 * i;
-      if (c < cend) {
-        load4(xr + 4 * c, xh[i]);
-        load4(dyr + 4 * c, gy[i]);
-        if (dres) load4(dres + (int64_t)row * D + 4 * c, rr[i]);
-      }
+  prefetch(row, 0);
+  float mu_next = row < M ? mean[row] : 0.f, rs_next = row < M ? rstd[row] : 0.f;
+  for (; row < M; row += stride, parity ^= 1) {
+    prefetch(row + stride, parity ^ 1);
+    const float mu = mu_next, rs = rs_next;
+    if (row + stride < M) {   // the next row's statistics travel with its operands, not after them
+      mu_next = mean[row + stride];
+      rs_next = rstd[row + stride];
     }
-    const float mu = mean[row], rs = rstd[row];
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // this row's copies (issued by this thread) have landed
+    float xh[NVH][4], gy[NVH][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NVH; ++i) {
       const int c = cbase + lane + 32 * i;
       if (c < cend) {
         float g[4];
+        load4(reinterpret_cast<const TX*>(slot(parity, 0, i)), xh[i]);
+        load4(reinterpret_cast<const TDY*>(slot(parity, 1, i)), gy[i]);
         load4(gamma + 4 * c, g);  // L1-resident
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -195,20 +231,26 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
       if (c < cend) {
         float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
-          if (dres) o[e] += rr[i][e];
-          ds[i][e] += o[e];
+        for (int e = 0; e < 4; ++e) o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
+        if (dres) {
+          float r[4];
+          load4(reinterpret_cast<const float*>(slot(parity, 2, i)), r);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] += r[e];
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ds[i][e] += o[e];
         store4(dx + (int64_t)row * D + 4 * c, o);
         if (dx_bf16) store4(dx_bf16 + (int64_t)row * D + 4 * c, o);
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (dgamma == nullptr) return;
-  float* sg = s_red;
-  float* sb = s_red + (size_t)npairs * D;
-  float* ss = s_red + (size_t)2 * npairs * D;
+  __syncthreads();  // the staging area becomes the reduction scratch
+  float* sg = reinterpret_cast<float*>(s_dyn);
+  float* sb = sg + (size_t)npairs * D;
+  float* ss = sg + (size_t)2 * npairs * D;
 #pragma unroll
   for (int i = 0; i < NVH; ++i) {
     const int c = cbase + lane + 32 * i;
@@ -293,11 +335,29 @@ extern "C" int favit_layernorm_bwd(const void* dy, favit_dtype dy_dtype, const v
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int pairs = 2;                                          // rows in flight per CTA (2 warps each)
-  const size_t smem = (size_t)3 * pairs * D * sizeof(float);   // <= 24 KiB
-  const unsigned blocks = (unsigned)max(1, min(ceil_div(M, pairs), 6 * num_sms()));
-#define LN_BWD_NV(TX, TDY, NVH)                                                                                  \
-  ln_bwd_kernel<TX, TDY, NVH><<<blocks, pairs * 64, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
-                                                                dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, M, D)
+  const int nvh_t = D <= 256 ? 1 : (D <= 512 ? 2 : (D <= 768 ? 3 : 4));
+  const size_t stage_bytes = (size_t)2 * 3 * nvh_t * 128 * 16;                       // <= 48 KiB
+  const size_t smem = max(stage_bytes, (size_t)3 * pairs * D * sizeof(float));
+// persistent grid = exactly the number of CTAs that are resident at once (queried, with the shared-memory carve-out
+// maximised): a second, partial wave of a persistent kernel would run at a fraction of the occupancy
+#define LN_BWD_NV(TX, TDY, NVH)                                                                                    \
+  do {                                                                                                             \
+    static int occ = 0;                                                                                            \
+    if (occ == 0) {                                                                                                \
+      FAVIT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<TX, TDY, NVH>,                                           \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));              \
+      FAVIT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<TX, TDY, NVH>,                                           \
+                                            cudaFuncAttributePreferredSharedMemoryCarveout,                        \
+                                            cudaSharedmemCarveoutMaxShared));                                      \
+      FAVIT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<TX, TDY, NVH>,            \
+                                                                     pairs * 64, smem));                           \
+      if (occ < 1) occ = 1;                                                                                        \
+    }                                                                                                              \
+    const unsigned blocks = (unsigned)max(1, min(ceil_div(M, pairs), occ * num_sms()));                            \
+    ln_bwd_kernel<TX, TDY, NVH><<<blocks, pairs * 64, smem, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, \
+                                                                  dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, \
+                                                                  dxsum, M, D);                                    \
+  } while (0)
 #define LN_BWD(TX, TDY)                           \
   do {                                            \
     if (D <= 256) LN_BWD_NV(TX, TDY, 1);          \
