@@ -24,10 +24,11 @@ _SIGS = {
     "favit_last_error": ([], C.c_char_p),
     "favit_launch_count": ([], _u64),
     "favit_mhla_attn_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
-    "favit_mhla_attn_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f,
+    "favit_colsum": ([_vp, _i, _vp, _i, _i, _i64, _vp], _i),
+    "favit_mhla_attn_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f,
                              _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
     "favit_linear_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp], _i),
-    "favit_linear_dgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp], _i),
+    "favit_linear_dgrad": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp], _i),
     "favit_linear_wgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp], _i),
     "favit_gemm_bf16_raw": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp], _i),
     "favit_layernorm_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp], _i),

@@ -23,6 +23,7 @@ struct Epilogue {
   int act = 0;                    // favit_epilogue
   int accumulate = 0;             // C += result (fp32 C only)
   int split_ok = 0;               // caller allows split-K (C is zeroed or being accumulated into)
+  float* colsum = nullptr;        // [N] fp32, accumulated: column sums of a bf16 C (CTA-pair kernel only)
 };
 
 // C[M,N] = A.B^T with the operand storage flags described in gemm_tcgen05.cu.

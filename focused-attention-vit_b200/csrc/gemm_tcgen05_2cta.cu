@@ -54,6 +54,7 @@ struct K2Params {
   int act;       // FAVIT_EPI_NONE / GELU (writes the pre-activation through tmC2) / DGELU_MUL (reads tmAux)
   int c_fp32;    // C element type: 1 = fp32 (box 32 x 32), 0 = bf16 (box 64 x 32)
   int reduce;    // accumulate into C with TMA reduce-add (split-K or accumulate)
+  float* colsum; // [N] fp32, accumulated: column sums of the bf16 output (plain / GELU' epilogues only)
 };
 
 // this lane's 32-column slice -> its row of a swizzled staging unit (bf16: 4 x 16-byte chunks at chunk offset `c4`)
@@ -314,6 +315,22 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             const int ucol = col - 32;
             if (lane == 0 && ucol < p.N) tma_store_2d(&tmC, outbuf_u32 + obuf * kUnit, ucol, row0);
             if (lane == 0) tma_store_commit();
+            if (p.colsum) {
+              // column sums of the staged 32 x 64 bf16 unit (the values exactly as stored): the bias gradient of the
+              // layer that consumes this gradient, without a second pass over the tensor.  Lane l owns columns 2l, 2l+1;
+              // rows past M hold exact zeros (TMA zero-fills A), so they add nothing.
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(ub + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) +
+                                                                       (lane & 3) * 4);
+                s0 += __uint_as_float(w2 << 16);
+                s1 += __uint_as_float(w2 & 0xffff0000u);
+              }
+              const int cc = ucol + 2 * lane;
+              if (cc < p.N) atomicAdd(p.colsum + cc, s0);
+              if (cc + 1 < p.N) atomicAdd(p.colsum + cc + 1, s1);
+            }
             obuf = (obuf + 1) % NOUT;
           }
         }
@@ -411,7 +428,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
 }  // namespace
 
 bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t lda, int64_t ldb) {
-  if (M < 2048 || N < 256 || K < 64) return false;                 // small problems: the 1-CTA kernel's narrower tiles
+  // small problems keep the 1-CTA kernel's narrower tiles; "large" = at least one full wave of 256 x 256 x 512 work
+  if (M < 256 || N < 256 || K < 64) return false;
+  if ((int64_t)ceil_div(M, 256) * ceil_div(N, 256) * ceil_div(K, 64) < 74 * 8) return false;
   if (e.residual != nullptr) return false;                          // fp32 residual epilogue stays on the 1-CTA kernel
   const int es = e.c_dtype == FAVIT_BF16 ? 2 : 4;
   if (((uintptr_t)e.c % 16) || ((e.ldc * es) % 16)) return false;   // TMA store pitch
@@ -420,6 +439,7 @@ bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t l
   if (e.act == FAVIT_EPI_DGELU_MUL && (e.c_dtype != FAVIT_BF16 || !e.aux || ((uintptr_t)e.aux % 16) || ((e.ldaux * 2) % 16)))
     return false;
   if (e.accumulate && e.c_dtype != FAVIT_F32) return false;
+  if (e.colsum && (e.c_dtype != FAVIT_BF16 || e.act == FAVIT_EPI_GELU)) return false;
   return true;
 }
 
@@ -477,6 +497,7 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.act = epi.act;
   kp.c_fp32 = c_fp32 ? 1 : 0;
   kp.reduce = (splits > 1 || epi.accumulate) ? 1 : 0;
+  kp.colsum = epi.colsum;
   const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
   return aux ? launch<true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
              : launch<false>(ta, tb, tcm, tc2, taux, kp, clusters, st);

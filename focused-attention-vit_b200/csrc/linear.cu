@@ -104,9 +104,9 @@ extern "C" int favit_linear_fwd(const void* x, const void* w, const float* bias,
   return tc::gemm_bf16(x, 0, ldx, w, 0, ldw, M, N, K, e, 0, 0, st);
 }
 
-extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, int M, int N, int K,
-                                  int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype, favit_dtype dx_dtype,
-                                  int epilogue, favit_stream stream) {
+extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, float* dx_colsum, int M,
+                                  int N, int K, int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype,
+                                  favit_dtype dx_dtype, int epilogue, favit_stream stream) {
   if (int rc = check_dims("linear_dgrad", M, N, K)) return rc;
   FAVIT_CHECK_ARG(dy && w && dx, "linear_dgrad: null dy/w/dx");
   FAVIT_CHECK_ARG(epilogue == FAVIT_EPI_NONE || (epilogue == FAVIT_EPI_DGELU_MUL && preact),
@@ -115,15 +115,24 @@ extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* pre
   // dX[m,k] = sum_n dY[m,n] W[n,k]: output M x K, reduction over N; W is stored [reduction][out] (MN-major B)
   if (dtype == FAVIT_F32) {
     FAVIT_CHECK_ARG(dx_dtype == FAVIT_F32, "linear_dgrad: the fp32 path is fp32 end to end");
-    return gemm_simt_launch((const float*)dy, (const float*)w, (float*)dx, nullptr, (const float*)preact, nullptr,
-                            nullptr, 0, M, K, N, lddy, 1, 1, ldw, lddx, epilogue, 1, 0, st);
+    int rc = gemm_simt_launch((const float*)dy, (const float*)w, (float*)dx, nullptr, (const float*)preact, nullptr,
+                              nullptr, 0, M, K, N, lddy, 1, 1, ldw, lddx, epilogue, 1, 0, st);
+    if (rc || !dx_colsum) return rc;
+    return launch_colsum<float>(dx, dx_colsum, M, K, lddx, st);
   }
   FAVIT_CHECK_ARG(dtype == FAVIT_BF16, "linear_dgrad: bad dtype");
   tc::Epilogue e;
   e.c = dx; e.ldc = lddx; e.c_dtype = dx_dtype;
   e.aux = preact; e.ldaux = lddx;
   e.act = epilogue;
-  return tc::gemm_bf16(dy, 0, lddy, w, 1, ldw, M, K, N, e, 0, 0, st);
+  // the CTA-pair kernel sums the columns of dX in its epilogue; otherwise one extra pass over dX
+  e.colsum = dx_colsum;
+  const bool fused = dx_colsum && tc::gemm_bf16_2cta_applicable(M, K, N, e, lddy, ldw);
+  if (!fused) e.colsum = nullptr;
+  int rc = tc::gemm_bf16(dy, 0, lddy, w, 1, ldw, M, K, N, e, 0, 0, st);
+  if (rc || !dx_colsum || fused) return rc;
+  if (dx_dtype == FAVIT_BF16) return launch_colsum<__nv_bfloat16>(dx, dx_colsum, M, K, lddx, st);
+  return launch_colsum<float>(dx, dx_colsum, M, K, lddx, st);
 }
 
 extern "C" int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
@@ -171,4 +180,13 @@ extern "C" int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const v
   e.c = c; e.ldc = ldc; e.c_dtype = c_dtype;
   e.split_ok = (splits != 1) ? 1 : 0;
   return tc::gemm_bf16(a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, M, N, K, e, bn, splits, (cudaStream_t)stream);
+}
+
+// out[n] += sum_m x[m,n]   (accumulates: zero `out` first for a plain column sum)
+extern "C" int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int64_t ld, favit_stream stream) {
+  FAVIT_CHECK_ARG(x && out && M > 0 && N > 0, "colsum: bad argument");
+  if (dtype == FAVIT_F32) return launch_colsum<float>(x, out, M, N, ld, (cudaStream_t)stream);
+  if (dtype == FAVIT_BF16) return launch_colsum<__nv_bfloat16>(x, out, M, N, ld, (cudaStream_t)stream);
+  set_error("colsum: bad dtype");
+  return FAVIT_ERR_ARG;
 }

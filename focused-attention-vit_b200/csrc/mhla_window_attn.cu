@@ -23,8 +23,8 @@ bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* m
 int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
                  int window, float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
 int attn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
-                 void* dq, void* dk, void* dv, float* delta, int B, int H, int N, int hd, int window, float scale,
-                 int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+                 void* dq, void* dk, void* dv, float* delta, float* colsum, int B, int H, int N, int hd, int window,
+                 float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
 
 namespace {
 
@@ -385,9 +385,12 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
   }
 }
 
+extern "C" int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int64_t ld, favit_stream stream);
+
 extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, const uint8_t* mask,
                                    const void* out, const float* lse, const void* dout, void* dq, void* dk,
-                                   void* dv, float* delta, int B, int H, int N, int hd, int window, float scale,
+                                   void* dv, float* delta, float* dqkv_colsum, int B, int H, int N, int hd, int window,
+                                   float scale,
                                    int64_t stride_b, int64_t stride_n, int64_t stride_h, favit_dtype dtype,
                                    float dropout_p, uint64_t seed, favit_stream stream) {
   (void)seed;
@@ -395,13 +398,25 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse && dout && dq && dk && dv && delta, "mhla_attn_bwd: null pointer");
   if (attn_mma_applicable(hd, window, dtype, mask))
-    return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, B, H, N, hd, window, scale, stride_b, stride_n,
-                        stride_h, (cudaStream_t)stream);
+    return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, dqkv_colsum, B, H, N, hd, window, scale, stride_b,
+                        stride_n, stride_h, (cudaStream_t)stream);
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == FAVIT_BF16) {
-    FAVIT_DISPATCH_HD(__nv_bfloat16, launch_bwd, q, k, v, mask, out, lse, dout, dq, dk, dv, delta, sh, st)
-  } else {
-    FAVIT_DISPATCH_HD(float, launch_bwd, q, k, v, mask, out, lse, dout, dq, dk, dv, delta, sh, st)
+  auto run = [&]() -> int {
+    if (dtype == FAVIT_BF16) {
+      FAVIT_DISPATCH_HD(__nv_bfloat16, launch_bwd, q, k, v, mask, out, lse, dout, dq, dk, dv, delta, sh, st)
+    } else {
+      FAVIT_DISPATCH_HD(float, launch_bwd, q, k, v, mask, out, lse, dout, dq, dk, dv, delta, sh, st)
+    }
+  };
+  rc = run();
+  if (rc || !dqkv_colsum) return rc;
+  // general path: the column sums (bias gradient of the qkv projection) take one more pass over dq, dk, dv
+  FAVIT_CHECK_ARG(stride_b == (int64_t)N * stride_n, "mhla_attn_bwd: dqkv_colsum needs batch-contiguous dq/dk/dv");
+  const void* parts[3] = {dq, dk, dv};
+  for (int t = 0; t < 3; ++t) {
+    rc = favit_colsum(parts[t], dtype, dqkv_colsum + (size_t)t * H * hd, B * N, H * hd, stride_n, stream);
+    if (rc) return rc;
   }
+  return FAVIT_OK;
 }

@@ -28,6 +28,7 @@ struct Shape {
   int64_t sb, sn, sh;  // q/k/v strides in elements (shared by dq/dk/dv)
   float scale_log2, scale;
   int tiles;           // 16-row tiles per sequence
+  float* colsum;       // backward only, may be null: [3 * H * hd] fp32 column sums of dq | dk | dv (accumulated)
 };
 
 struct WindowRow {
@@ -142,6 +143,25 @@ __device__ __forceinline__ void store_rows(const uint8_t* tile, int lane, F dst_
     __nv_bfloat16* dst = dst_row(r);
     if (dst) *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(tile + tile_off<HD>(r, c));
   }
+}
+
+// column sums of a staged 16-row tile (rows past the end of the sequence hold exact zeros) added to dst[0..HD)
+template <int HD>
+__device__ __forceinline__ void tile_colsum(const uint8_t* tile, int lane, float* dst) {
+  constexpr int CPL = HD / 32;  // columns per lane
+  if (CPL == 0) return;
+  float s[CPL > 0 ? CPL : 1];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) s[c] = 0.f;
+  const int c0 = lane * CPL;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const uint8_t* p = tile + tile_off<HD>(r, c0 >> 3) + (c0 & 7) * 2;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) s[c] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p + 2 * c));
+  }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) atomicAdd(dst + c0 + c, s[c]);
 }
 
 // ---- key slots of a query tile -----------------------------------------------------------------------------------
@@ -396,6 +416,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dq_kernel(
   stage_acc<HD>(sO, acc, sh.scale, sh.scale, lane);
   __syncwarp();
   store_rows<HD>(sO, lane, [&](int r) { return (i0 + r < N) ? dq + base + (int64_t)(i0 + r) * sh.sn : nullptr; });
+  if (sh.colsum) tile_colsum<HD>(sO, lane, sh.colsum + h * HD);
   if ((lane & 3) == 0) {
     float* dl = delta + ((int64_t)b * sh.H + h) * N;
     if (ok0) dl[i0 + r0] = d0;
@@ -521,6 +542,10 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dkv_kernel(
   __syncwarp();
   store_rows<HD>(sV, lane, [&](int r) { return (j0 + r < N) ? dv + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
   store_rows<HD>(sK, lane, [&](int r) { return (j0 + r < N) ? dk + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
+  if (sh.colsum) {
+    tile_colsum<HD>(sK, lane, sh.colsum + (sh.H + h) * HD);
+    tile_colsum<HD>(sV, lane, sh.colsum + (2 * sh.H + h) * HD);
+  }
 }
 
 template <typename K>
@@ -576,7 +601,7 @@ bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* m
 
 int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
                  int window, float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
-  Shape sh{B, H, N, window, sb, sn, shh, scale * kLog2e, scale, ceil_div(N, 16)};
+  Shape sh{B, H, N, window, sb, sn, shh, scale * kLog2e, scale, ceil_div(N, 16), nullptr};
   switch (hd) {
     case 32: return launch_fwd<32>(q, k, v, out, lse, sh, st);
     case 64: return launch_fwd<64>(q, k, v, out, lse, sh, st);
@@ -585,9 +610,9 @@ int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* 
 }
 
 int attn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
-                 void* dq, void* dk, void* dv, float* delta, int B, int H, int N, int hd, int window, float scale,
-                 int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
-  Shape sh{B, H, N, window, sb, sn, shh, scale * kLog2e, scale, ceil_div(N, 16)};
+                 void* dq, void* dk, void* dv, float* delta, float* colsum, int B, int H, int N, int hd, int window,
+                 float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
+  Shape sh{B, H, N, window, sb, sn, shh, scale * kLog2e, scale, ceil_div(N, 16), colsum};
   const bool wide = (17 + 4 * (window >> 1)) > 32;  // query slots a key tile may need
 #define FAVIT_BWD(HD)                                                                                  \
   return wide ? launch_bwd<HD, 6>(q, k, v, o, lse, dout, dq, dk, dv, delta, sh, st)                    \

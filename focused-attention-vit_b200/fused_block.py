@@ -82,15 +82,15 @@ def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, 
     dw2, db2 = raw.linear_wgrad(g_c, h, want_bias=gsum is None)
     if gsum is not None:
         db2 = gsum
-    dhpre = raw.linear_dgrad(g_c, w2, hpre, cd)
-    dw1, db1 = raw.linear_wgrad(dhpre, xn2)
+    dhpre, db1 = raw.linear_dgrad(g_c, w2, hpre, cd, colsum=True)   # fc1's bias gradient from the GELU' epilogue
+    dw1, _ = raw.linear_wgrad(dhpre, xn2, want_bias=False)
     dxn2 = raw.linear_dgrad(dhpre, w1, None, cd)
     g2, g2_b, dg2, dbt2, dbp = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf)   # dbp = column sums of g2
     g2_c = g2_b if bf else g2
     dwp, _ = raw.linear_wgrad(g2_c, o, want_bias=False)
     do = raw.linear_dgrad(g2_c, wproj, None, cd)
-    dqkv = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window)
-    dwq, dbq = raw.linear_wgrad(dqkv, xn)
+    dqkv, dbq = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window)   # qkv bias gradient from the attention backward
+    dwq, _ = raw.linear_wgrad(dqkv, xn, want_bias=False)
     dxn = raw.linear_dgrad(dqkv, wqkv, None, cd)
     g0, g0_b, dg1, dbt1, g0sum = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf)
     _GRAD_BF16.clear()                          # at most one hand-over is alive

@@ -105,7 +105,7 @@ def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: tor
         preact = preact.contiguous()
     if M == 0:
         return dx
-    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), M, N, K, _ld(dy), _ld(w), K, _dt(dy),
+    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), None, M, N, K, _ld(dy), _ld(w), K, _dt(dy),
                                     _DT[out_dtype], L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _stream())
     L.check(rc, "favit_linear_dgrad")
     return dx
@@ -236,7 +236,7 @@ def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: i
     es = qkv.element_size()
     dq = dqkv.data_ptr()
     rc = L.call("attn_bwd", 8.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_bwd, q, k, v, _p(mask), _p(out), _p(lse), _p(dout), dq, dq + H * hd * es,
-                                     dq + 2 * H * hd * es, _p(delta), B, H, N, hd, window, float(hd) ** -0.5,
+                                     dq + 2 * H * hd * es, _p(delta), None, B, H, N, hd, window, float(hd) ** -0.5,
                                      sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
     L.check(rc, "favit_mhla_attn_bwd")
     return dqkv

@@ -33,14 +33,17 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[
     return y, pre
 
 
-def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype) -> Tensor:
+def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype, colsum: bool = False):
+    """dx = dy @ w (* gelu'(preact)); with colsum also the fp32 column sums of dx (returns (dx, sums))."""
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
-    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), M, N, K,
-                N, K, K, _DT[dy.dtype], _DT[out_dtype], L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _s())
+    sums = torch.zeros((K,), dtype=torch.float32, device=dy.device) if colsum else None
+    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), _p(sums),
+                M, N, K, N, K, K, _DT[dy.dtype], _DT[out_dtype],
+                L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _s())
     L.check(rc, "favit_linear_dgrad")
-    return dx
+    return (dx, sums) if colsum else dx
 
 
 def linear_wgrad(dy: Tensor, x: Tensor, want_bias: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
@@ -103,13 +106,15 @@ def attn_fwd(qkv: Tensor, B: int, N: int, H: int, hd: int, window: int):
 
 
 def attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, H: int, hd: int, window: int):
+    """Returns (dqkv, fp32 column sums of dqkv = the qkv bias gradient)."""
     es = qkv.element_size()
     dqkv = torch.empty_like(qkv)
+    sums = torch.zeros((3 * H * hd,), dtype=torch.float32, device=qkv.device)
     delta = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     off = H * hd * es
     rc = L.call("attn_bwd", 8.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_bwd, base, base + off, base + 2 * off,
-                None, _p(out), _p(lse), _p(dout), dbase, dbase + off, dbase + 2 * off, _p(delta), B, H, N, hd, window,
-                float(hd) ** -0.5, N * 3 * H * hd, 3 * H * hd, hd, _DT[qkv.dtype], 0.0, 0, _s())
+                None, _p(out), _p(lse), _p(dout), dbase, dbase + off, dbase + 2 * off, _p(delta), _p(sums), B, H, N, hd,
+                window, float(hd) ** -0.5, N * 3 * H * hd, 3 * H * hd, hd, _DT[qkv.dtype], 0.0, 0, _s())
     L.check(rc, "favit_mhla_attn_bwd")
-    return dqkv
+    return dqkv, sums

@@ -71,10 +71,12 @@ int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, const uint8
 
 /* Backward of the above (the reference relies on autograd: gather -> scatter_add_, bmm, softmax).
  * dout: [B,N,H,hd] contiguous.  dq,dk,dv use the same strides as q,k,v (written in place into a packed
- * dqkv buffer).  delta: fp32 workspace [B,H,N]. */
+ * dqkv buffer).  delta: fp32 workspace [B,H,N].  dqkv_colsum (may be NULL): [3*H*hd] fp32, ACCUMULATED with the column
+ * sums of dq | dk | dv over all B*N rows — the bias gradient of the qkv projection (mhla.py:100), produced while the
+ * gradient tiles are still in shared memory. */
 int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, const uint8_t* mask,
                         const void* out, const float* lse, const void* dout,
-                        void* dq, void* dk, void* dv, float* delta,
+                        void* dq, void* dk, void* dv, float* delta, float* dqkv_colsum,
                         int B, int H, int N, int hd, int window, float scale,
                         int64_t stride_b, int64_t stride_n, int64_t stride_h,
                         favit_dtype dtype, float dropout_p, uint64_t seed, favit_stream stream);
@@ -93,7 +95,9 @@ int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, const uint8
  *      bias, residual, preact_out may be NULL.  y_dtype/res_dtype select fp32 or bf16 for Y / residual
  *      (the fp32 residual stream of a bf16 block); they must be FAVIT_F32 when dtype is FAVIT_F32.
  * favit_linear_dgrad: dX[M,K] = dY[M,N] . W[N,K]   (epilogue FAVIT_EPI_DGELU_MUL: * gelu'(preact[M,K]),
- *      preact has dX's leading dimension)
+ *      preact has dX's leading dimension).  dx_colsum (may be NULL): [K] fp32, ACCUMULATED with the column sums of dX
+ *      as stored — dX is the output gradient of the layer below, so this is that layer's bias gradient, produced in
+ *      the GEMM epilogue instead of a second pass over dX.
  * favit_linear_wgrad: dW[N,K] (+)= dY[M,N]^T . X[M,K]  and, when db != NULL, db[N] (+)= column sums of dY.
  *      accumulate == 0 overwrites (the call zero-fills first), != 0 adds to the existing values.
  *      Split-K partial sums are combined with fp32 atomics, so the last bits may vary between runs.
@@ -103,13 +107,16 @@ int favit_linear_fwd(const void* x, const void* w, const float* bias, const void
                      int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
                      int epilogue, favit_stream stream);
 
-int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, int M, int N, int K,
-                       int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype, favit_dtype dx_dtype,
+int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, float* dx_colsum, int M, int N,
+                       int K, int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype, favit_dtype dx_dtype,
                        int epilogue, favit_stream stream);
 
 int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
                        int64_t lddy, int64_t ldx, int64_t lddw, favit_dtype dtype, int accumulate,
                        favit_stream stream);
+
+/* out[n] += sum over the M rows of x[m,n] (x row-major with leading dimension ld): a bias gradient. */
+int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int64_t ld, favit_stream stream);
 
 /* Test / tuning hook: C[M,N] = A.B^T through the tcgen05 kernel with explicit operand storage
  * (a_mn / b_mn: 0 = reduction dimension contiguous, 1 = M/N dimension contiguous), tile width

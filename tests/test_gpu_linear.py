@@ -91,3 +91,29 @@ def test_linear_epilogues(dtype, M, K, N):
     pk = pre_k.double().requires_grad_(True)
     torch.nn.functional.gelu(pk).backward(dy.double() @ w.double())
     assert_close(dx, pk.grad, dtype, "dgelu", factor=2.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(4200, 648, 256), (300, 200, 136)], ids=["cta_pair_fused", "small_separate_pass"])
+def test_dgrad_column_sums(M, N, K):
+    """dx_colsum of favit_linear_dgrad == column sums of the dX it stored (fused in the CTA-pair epilogue for large
+    shapes, a separate reduction otherwise)."""
+    from favit_b200 import raw
+    torch.manual_seed(3)
+    dy = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    pre = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    for preact in (None, pre):
+        dx, sums = raw.linear_dgrad(dy, w, preact, torch.bfloat16, colsum=True)
+        ref = dx.double().sum(dim=0)
+        assert rel_err(sums, ref, floor=1e-3 * float(dx.float().abs().max()) * M ** 0.5) < 1e-4
+
+
+def test_attention_backward_column_sums():
+    from favit_b200 import raw
+    B, N, H, hd, W = 3, 65, 3, 64, 7
+    qkv = torch.randn(B * N, 3 * H * hd, device="cuda").to(torch.bfloat16)
+    do = torch.randn(B * N, H * hd, device="cuda").to(torch.bfloat16)
+    o, lse = raw.attn_fwd(qkv, B, N, H, hd, W)
+    dqkv, sums = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, W)
+    ref = dqkv.double().sum(dim=0)
+    assert rel_err(sums, ref, floor=1e-3 * float(dqkv.float().abs().max()) * (B * N) ** 0.5) < 1e-4

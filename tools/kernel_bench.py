@@ -111,7 +111,7 @@ def main():
         do = rnd(M, D)
         rec("attn fwd", timeit(lambda i: raw.attn_fwd(qkv[i], B, N, H, hd, a.W), a.iters, nbuf), None, 4.0 * M * D * 2)
         o, lse = raw.attn_fwd(qkv[0], B, N, H, hd, a.W)
-        rec("attn bwd", timeit(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, hd, a.W), a.iters, nbuf), None,
+        rec("attn bwd", timeit(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, hd, a.W)[0], a.iters, nbuf), None,
             8.0 * M * D * 2)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)
