@@ -107,49 +107,82 @@ def _(g, x, ln1_w, wqkv, wproj, ln2_w, w1, w2, xn, mu1, rs1, qkv, o, lse, x2, xn
     return [e(x), v(D), v(D), e(wqkv), v(wqkv.shape[0]), e(wproj), v(D), v(D), v(D), e(w1), v(w1.shape[0]), e(w2), v(D)]
 
 
+@torch.library.custom_op("favit::latent_fold_fwd", mutates_args=())
+def latent_fold_fwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, proj_b: Tensor, lat_w: Tensor, lat_b: Tensor, H: int,
+                    cd: torch.dtype) -> List[Tensor]:
+    """[wqkv' (cd), bqkv' (fp32), wproj' (cd), bproj' (fp32)] with latent_proj folded in (mhla.py:105-106)."""
+    return list(raw.fold_fwd(qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, H, cd))
+
+
+@latent_fold_fwd.register_fake
+def _(qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, H, cd):
+    f32 = torch.float32
+    return [qkv_w.new_empty(qkv_w.shape, dtype=cd), qkv_b.new_empty(qkv_b.shape, dtype=f32),
+            proj_w.new_empty(proj_w.shape, dtype=cd), proj_b.new_empty(proj_b.shape, dtype=f32)]
+
+
+@torch.library.custom_op("favit::latent_fold_bwd", mutates_args=("dwqkv", "dbqkv", "dwproj"))
+def latent_fold_bwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, lat_w: Tensor, lat_b: Tensor, dwqkv: Tensor,
+                    dbqkv: Tensor, dwproj: Tensor, dbproj: Tensor, H: int) -> List[Tensor]:
+    """dwqkv / dbqkv / dwproj: gradients of the folded weights, rewritten IN PLACE into the gradients of qkv.weight,
+    qkv.bias, proj.weight.  Returns [dlatent_w, dlatent_b]."""
+    return list(raw.fold_bwd(qkv_w, qkv_b, proj_w, lat_w, lat_b, dwqkv, dbqkv, dwproj, dbproj, H))
+
+
+@latent_fold_bwd.register_fake
+def _(qkv_w, qkv_b, proj_w, lat_w, lat_b, dwqkv, dbqkv, dwproj, dbproj, H):
+    return [lat_w.new_empty(lat_w.shape, dtype=torch.float32), lat_b.new_empty(lat_b.shape, dtype=torch.float32)]
+
+
 class FusedBlockFn(torch.autograd.Function):
-    """x [B,N,D] fp32 + block parameters (fp32 masters; qkv/proj already latent-folded) -> [B,N,D] fp32."""
+    """x [B,N,D] fp32 + the block's fp32 master parameters -> [B,N,D] fp32."""
 
     @staticmethod
-    def forward(ctx, x, ln1_w, ln1_b, wqkv, bqkv, wproj, bproj, ln2_w, ln2_b, w1, b1, w2, b2, H, window, eps1, eps2,
-                cd):
+    def forward(ctx, x, ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, ln2_w, ln2_b, w1, b1, w2, b2, H,
+                window, eps1, eps2, cd):
         B, N, D = x.shape
         x2d = x.reshape(B * N, D)
         if not x2d.is_contiguous():
             x2d = x2d.contiguous()
-        c = (lambda t: t.detach().to(cd)) if cd != torch.float32 else (lambda t: t.detach())
+        c = (lambda t: t.detach().to(cd)) if cd != torch.float32 else (lambda t: t.detach().contiguous())
         f = lambda t: t.detach().float().contiguous()
-        wq_c, wp_c, w1_c, w2_c = c(wqkv), c(wproj), c(w1), c(w2)
-        outs = block_fwd(x2d.detach(), f(ln1_w), f(ln1_b), wq_c, f(bqkv), wp_c, f(bproj), f(ln2_w), f(ln2_b), w1_c,
-                         f(b1), w2_c, f(b2), B, N, H, window, eps1, eps2)
+        raw_p = [f(qkv_w), f(qkv_b), f(proj_w), f(proj_b), f(lat_w), f(lat_b)]
+        wq_c, bq, wp_c, bp = latent_fold_fwd(*raw_p, H, cd)
+        w1_c, w2_c = c(w1), c(w2)
+        outs = block_fwd(x2d.detach(), f(ln1_w), f(ln1_b), wq_c, bq, wp_c, bp, f(ln2_w), f(ln2_b), w1_c, f(b1), w2_c,
+                         f(b2), B, N, H, window, eps1, eps2)
         x3 = outs[0]
-        ctx.save_for_backward(x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *outs[1:])
+        ctx.save_for_backward(x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, qkv_w, qkv_b, proj_w, lat_w, lat_b, *outs[1:])
         ctx.dims = (B, N, H, window)
         return x3.view(B, N, D)
 
     @staticmethod
     def backward(ctx, g):
-        x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *saved = ctx.saved_tensors
+        x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, qkv_w, qkv_b, proj_w, lat_w, lat_b, *saved = ctx.saved_tensors
         B, N, H, window = ctx.dims
         D = x2d.shape[1]
         g2d = g.reshape(B * N, D)
         if g2d.dtype != torch.float32:
             g2d = g2d.float()
-        outs = block_bwd(g2d, x2d, ln1_w.detach().float().contiguous(), wq_c, wp_c,
-                         ln2_w.detach().float().contiguous(), w1_c, w2_c, *saved, B, N, H, window)
-        dx = outs[0].view(B, N, D)
-        return (dx, *outs[1:], None, None, None, None, None)
+        f = lambda t: t.detach().float().contiguous()
+        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = block_bwd(
+            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window)
+        # gradients of the folded qkv / proj weights -> qkv.weight, qkv.bias, proj.weight (in place) + latent_proj
+        dlw, dlb = latent_fold_bwd(f(qkv_w), f(qkv_b), f(proj_w), f(lat_w), f(lat_b), dwq, dbq, dwp, dbp, H)
+        return (dx.view(B, N, D), dln1_w, dln1_b, dwq, dbq, dwp, dbp, dlw, dlb, dln2_w, dln2_b, dw1, db1, dw2, db2,
+                None, None, None, None, None)
 
 
-def fused_block(x, ln1, attn_folded, ln2, fc1, fc2, num_heads: int, window: int, compute_dtype: torch.dtype):
-    """attn_folded = (wqkv, bqkv, wproj, bproj) fp32 tensors (autograd-connected to qkv / proj / latent_proj)."""
-    wqkv, bqkv, wproj, bproj = attn_folded
-    return FusedBlockFn.apply(x, ln1.weight, ln1.bias, wqkv, bqkv, wproj, bproj, ln2.weight, ln2.bias, fc1.weight,
-                              fc1.bias, fc2.weight, fc2.bias, num_heads, window, ln1.eps, ln2.eps, compute_dtype)
+def fused_block(x, ln1, attn, ln2, fc1, fc2, compute_dtype: torch.dtype):
+    """attn: a MultiHeadLatentAttention module (qkv / proj / latent_proj parameters are read directly)."""
+    return FusedBlockFn.apply(x, ln1.weight, ln1.bias, attn.qkv.weight, attn.qkv.bias, attn.proj.weight,
+                              attn.proj.bias, attn.latent_proj.weight, attn.latent_proj.bias, ln2.weight, ln2.bias,
+                              fc1.weight, fc1.bias, fc2.weight, fc2.bias, attn.num_heads, attn.window_size, ln1.eps,
+                              ln2.eps, compute_dtype)
 
 
 def fusable(x: Tensor, attn, mlp_dropout_p: float, training: bool, attention_mask, compute_dtype, hidden: int) -> bool:
-    """Conditions under which the block runs as the two fused ops (otherwise the caller composes the unfused ops)."""
+    """Conditions under which the block runs as the fused ops (otherwise the caller composes the unfused ops)."""
     if attention_mask is not None or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:
         return False
     if training and (mlp_dropout_p > 0 or attn.attn_dropout.p > 0):
@@ -157,7 +190,7 @@ def fusable(x: Tensor, attn, mlp_dropout_p: float, training: bool, attention_mas
     D = x.shape[-1]
     if compute_dtype not in (torch.bfloat16, torch.float32):
         return False
-    if attn.head_dim not in (16, 32, 64, 128) or D % 8 or D > 1024 or hidden % 8:
+    if attn.head_dim not in (16, 32, 64) or D % 8 or D > 1024 or hidden % 8:
         return False
     if attn.window_size % 2 == 0 and x.shape[1] > attn.window_size:
         return False

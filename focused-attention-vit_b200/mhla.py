@@ -126,13 +126,8 @@ class MHLATransformerBlock(nn.Module):
         cd = compute_dtype(x)
         if fused_block.fusable(x, self.attn, self.mlp[2].p, self.training, attention_mask, cd,
                                self.mlp[0].out_features):
-            a = self.attn
             with torch.autocast("cuda", enabled=False):
-                folded = fold_latent(a.qkv.weight.float(), a.qkv.bias.float(), a.proj.weight.float(),
-                                     a.proj.bias.float(), a.latent_proj.weight.float(), a.latent_proj.bias.float(),
-                                     a.num_heads)
-                return fused_block.fused_block(x, self.norm1, folded, self.norm2, self.mlp[0], self.mlp[3],
-                                               a.num_heads, a.window_size, cd)
+                return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp[0], self.mlp[3], cd)
         x = x + self.attn(self.norm1(x), attention_mask)
         x = x + self.mlp(self.norm2(x))
         return x

@@ -90,13 +90,8 @@ class TransformerBlock(nn.Module):
             if fused_block.fusable(x, self.attn, self.mlp.dropout.p, self.training, attention_mask, cd,
                                    self.mlp.fc1.out_features):
                 # whole block as two favit ops (LN, GEMMs with fused bias/GELU/residual, window attention)
-                a = self.attn
                 with torch.autocast("cuda", enabled=False):
-                    folded = fold_latent(a.qkv.weight.float(), a.qkv.bias.float(), a.proj.weight.float(),
-                                         a.proj.bias.float(), a.latent_proj.weight.float(),
-                                         a.latent_proj.bias.float(), a.num_heads)
-                    return fused_block.fused_block(x, self.norm1, folded, self.norm2, self.mlp.fc1, self.mlp.fc2,
-                                                   a.num_heads, a.window_size, cd)
+                    return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp.fc1, self.mlp.fc2, cd)
         x_norm = self.norm1(x)
         if self.use_mhla:
             attn_output = self.attn(x_norm, attention_mask)

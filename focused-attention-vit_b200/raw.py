@@ -118,3 +118,33 @@ def attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int
                 window, float(hd) ** -0.5, N * 3 * H * hd, 3 * H * hd, hd, _DT[qkv.dtype], 0.0, 0, _s())
     L.check(rc, "favit_mhla_attn_bwd")
     return dqkv, sums
+
+
+def fold_fwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, proj_b: Tensor, lat_w: Tensor, lat_b: Tensor, H: int,
+             cd: torch.dtype):
+    """fp32 masters -> (wqkv' [3D,D] cd, bqkv' [3D] fp32, wproj' [D,D] cd, bproj' [D] fp32) with latent_proj folded in."""
+    D = proj_w.shape[0]
+    hd = D // H
+    dev = qkv_w.device
+    wq = torch.empty((3 * D, D), dtype=cd, device=dev)
+    wp = torch.empty((D, D), dtype=cd, device=dev)
+    bq = torch.empty((3 * D,), dtype=torch.float32, device=dev)
+    bp = torch.empty((D,), dtype=torch.float32, device=dev)
+    rc = L.call("fold", 0.0, L.lib().favit_latent_fold_fwd, _p(qkv_w), _p(qkv_b), _p(proj_w), _p(proj_b), _p(lat_w),
+                _p(lat_b), _p(wq), _p(bq), _p(wp), _p(bp), H, hd, _DT[cd], _s())
+    L.check(rc, "favit_latent_fold_fwd")
+    return wq, bq, wp, bp
+
+
+def fold_bwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, lat_w: Tensor, lat_b: Tensor, dwqkv: Tensor, dbqkv: Tensor,
+             dwproj: Tensor, dbproj: Tensor, H: int):
+    """In place: dwqkv / dbqkv / dwproj become the gradients of qkv.weight / qkv.bias / proj.weight.
+    Returns (dlat_w, dlat_b)."""
+    D = proj_w.shape[0]
+    hd = D // H
+    dlw = torch.empty((hd, hd), dtype=torch.float32, device=qkv_w.device)
+    dlb = torch.empty((hd,), dtype=torch.float32, device=qkv_w.device)
+    rc = L.call("fold", 0.0, L.lib().favit_latent_fold_bwd, _p(qkv_w), _p(qkv_b), _p(proj_w), _p(lat_w), _p(lat_b),
+                _p(dwqkv), _p(dbqkv), _p(dwproj), _p(dbproj), _p(dlw), _p(dlb), H, hd, _s())
+    L.check(rc, "favit_latent_fold_bwd")
+    return dlw, dlb

@@ -126,6 +126,20 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
                         favit_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Latent-projection fold — replaces the two per-token Linear(hd, hd) applications of models/mhla.py:105-106 by a
+ * per-step transformation of the qkv / proj WEIGHTS (exact): fwd writes the folded weights in the GEMM
+ * operand dtype plus fp32 folded biases; bwd maps the gradients of the folded weights back to qkv.weight, qkv.bias,
+ * proj.weight (in place) and produces latent_proj.weight / latent_proj.bias gradients.  All inputs fp32; hd <= 64.
+ * ---------------------------------------------------------------------------------------------- */
+int favit_latent_fold_fwd(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
+                          const float* lat_w, const float* lat_b, void* wqkv_c, float* bqkv, void* wproj_c,
+                          float* bproj, int H, int hd, favit_dtype out_dtype, favit_stream stream);
+
+int favit_latent_fold_bwd(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* lat_w,
+                          const float* lat_b, float* dwqkv, float* dbqkv, float* dwproj, const float* dbproj,
+                          float* dlat_w, float* dlat_b, int H, int hd, favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LayerNorm around the attention / MLP — "next" row: nn.LayerNorm at models/vit_mhla.py:88,107
  * (norm1 / norm2 of the block) and its autograd.  fp32 statistics; D % 4 == 0, D <= 1024.
  *
