@@ -27,8 +27,18 @@ class GradAllReducer:
             enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.enabled = enabled
         self.world = dist.get_world_size(process_group) if self.enabled else 1
-        cap = int(bucket_mb * (1 << 20)) // 4
         self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._size = []
+        self._pending = []
+        self._works = []
+        self._handles = []
+        self.overlap = True
+        if not self.enabled:
+            # single process: no flat buckets; gradients are dropped (set to None) every step so that autograd hands
+            # its freshly produced tensors over instead of adding them into zero-filled buffers
+            return
+        cap = int(bucket_mb * (1 << 20)) // 4
         self._bucket_of = {}
         self._size = []
         cur: List[torch.nn.Parameter] = []
@@ -65,6 +75,10 @@ class GradAllReducer:
 
     # -- per step ---------------------------------------------------------------------------------
     def zero_grad(self) -> None:
+        if not self.enabled:
+            for p in self.params:
+                p.grad = None
+            return
         for b in self.buckets:
             b.zero_()
         self._pending = list(self._size)
@@ -106,4 +120,4 @@ class GradAllReducer:
 
     @property
     def grad_bytes(self) -> int:
-        return sum(b.numel() * 4 for b in self.buckets)
+        return sum(p.numel() * 4 for p in self.params)
