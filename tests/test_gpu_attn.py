@@ -21,6 +21,13 @@ CASES = [
     (1, 2, 17, 64, 31, False),    # C2 tokens with a window wider than the sequence
     (1, 12, 197, 64, 7, False),   # C4 shape, one image
     (2, 2, 10, 64, 7, True),
+    (1, 2, 257, 64, 7, False),    # three chunks in the chunk-staged backward (N >= 64)
+    (1, 2, 130, 64, 15, False),   # two chunks, wide window: halo + edge rows + 48 query slots per key tile
+    (1, 1, 100, 32, 7, False),
+    (1, 1, 72, 128, 3, False),
+    (2, 1, 64, 64, 1, False),
+    (1, 1, 128, 64, 7, False),    # chunk boundary == sequence end
+    (1, 1, 129, 64, 7, False),    # a one-row second chunk
     (1, 2, 3, 64, 4, False),      # even window allowed when N <= W
     (1, 2, 4, 128, 4, False),
 ]
