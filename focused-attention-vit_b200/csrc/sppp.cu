@@ -10,12 +10,25 @@
 //                     insertion order of the reference's dict                        (sppp.py:123-126)
 //   per-slot patch lists are ascending patch ids                                     (sppp.py:126)
 //
-// All three kernels are HBM-bound byte movers: labels are read once with full 128-byte lines per patch row,
-// embeddings are read once with 16-byte vector loads through a CSR of patches per slot (no atomics, fixed
-// summation order), gradients are a pure gather.
+// All kernels are HBM-bound byte movers and are built around bytes in flight, not arithmetic:
+//   dominant : one warp per patch, 16-byte label loads, one vote for single-label patches, else a count per
+//              distinct label (few per patch)
+//   slots    : one CTA per image in shared memory: first occurrence of each dominant label, prefix count of the
+//              leaders, rank inside the slot -> slot ids, counts and the CSR, a handful of barriers per image
+//   pool fwd : one CTA per (image, 128-byte column slice); the [P x 128 B] tile arrives by TMA
+//              (cp.async.bulk.tensor, mbarrier) while the CSR is fetched, then each (slot, 8-byte column group)
+//              thread sums its patches out of shared memory in ascending patch order (deterministic, no atomics)
+//   pool bwd : one CTA per (image, 64-column slice); the R pre-divided gradient rows sit in shared memory and every
+//              patch row is one 16-byte store per thread
+// The older warp-per-item kernels remain as the fallback for shapes the tiled ones do not take (odd strides, huge R).
+#include <cuda.h>
 #include <limits.h>
 
+#include <algorithm>
+#include <mutex>
+
 #include "favit_common.cuh"
+#include "tcgen05_ptx.cuh"
 
 namespace favit {
 namespace {
@@ -267,9 +280,723 @@ __global__ void __launch_bounds__(256) sppp_pool_bwd_kernel(const TIn* __restric
   }
 }
 
+// =====================================================================================================
+// Tiled kernels (the fast path)
+// =====================================================================================================
+
+// ---- dominant label, vector loads --------------------------------------------------------------------
+// One warp per patch; PS in {8, 16, 32}: the PS*PS labels are held as NV = PS*PS/32 int64 per lane, fetched as
+// 16-byte pairs (needs an even image width and a 16-byte aligned map).  A patch covered by one label (the
+// common case inside a superpixel) costs one vote.  Otherwise labels are counted one distinct value per round,
+// candidates taken in whatever order lanes hold them, ties resolved towards the smaller id (sppp.py:117-120).
+template <int PS>
+__global__ void __launch_bounds__(256) sppp_dominant_vec_kernel(const int64_t* __restrict__ labels,
+                                                                int64_t* __restrict__ dom, int B, int img_h,
+                                                                int img_w, int grid) {
+  constexpr int NV = PS * PS / 32;             // labels per lane
+  constexpr int NP = NV / 2;                   // 16-byte pairs per lane
+  constexpr int PAIRS_PER_ROW = PS / 2;        // lanes covering one patch row
+  constexpr int ROWS_PER_LOAD = 32 / PAIRS_PER_ROW;
+  const int P = grid * grid;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= (int64_t)B * P) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(warp / P);
+  const int p = (int)(warp - (int64_t)b * P);
+  const int pi = p / grid, pj = p - pi * grid;
+  const int64_t* src = labels + ((int64_t)b * img_h + (int64_t)pi * PS + lane / PAIRS_PER_ROW) * img_w +
+                       (int64_t)pj * PS + 2 * (lane % PAIRS_PER_ROW);
+  long long vals[NV];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const longlong2 v = __ldcs(reinterpret_cast<const longlong2*>(src + (int64_t)k * ROWS_PER_LOAD * img_w));
+    vals[2 * k] = v.x;
+    vals[2 * k + 1] = v.y;
+  }
+  const long long v0 = __shfl_sync(0xffffffffu, vals[0], 0);
+  bool differs = false;
+#pragma unroll
+  for (int t = 0; t < NV; ++t) differs |= vals[t] != v0;
+  if (!__any_sync(0xffffffffu, differs)) {
+    if (lane == 0) dom[warp] = v0;
+    return;
+  }
+  unsigned alive = NV == 32 ? 0xffffffffu : ((1u << NV) - 1u);
+  int remaining = PS * PS, best_cnt = 0;
+  long long best_label = 0;
+  while (remaining > 0 && remaining >= best_cnt) {
+    const unsigned has = __ballot_sync(0xffffffffu, alive != 0u);
+    long long mine = 0;
+#pragma unroll
+    for (int t = NV - 1; t >= 0; --t)
+      if ((alive >> t) & 1u) mine = vals[t];
+    const long long cand = __shfl_sync(0xffffffffu, mine, __ffs(has) - 1);
+    int c = 0;
+#pragma unroll
+    for (int t = 0; t < NV; ++t)
+      if (((alive >> t) & 1u) && vals[t] == cand) {
+        ++c;
+        alive &= ~(1u << t);
+      }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c > best_cnt || (c == best_cnt && cand < best_label)) {
+      best_cnt = c;
+      best_label = cand;
+    }
+    remaining -= c;
+  }
+  if (lane == 0) dom[warp] = best_label;
+}
+
+// ---- slots: one CTA per image, everything in shared memory ----------------------------------------------
+// first[i]   = first run whose label equals that of run i    (run i is a "leader" when first[i] == i)
+// slot(leader) = number of leaders before it               (= dict insertion order, sppp.py:123-126)
+// slot[p]    = slot(first[run(p)]);  counts by shared-memory integer atomics;  offsets = exclusive scan of counts
+// order      = patches grouped by slot, ascending inside a slot
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();  // s_warp may still be read from the previous call
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int w = lane < nw ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += y;
+    }
+    if (lane < nw) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + incl - v;
+}
+
+// Works on RUNS of equal consecutive dominant labels (superpixels are spatially coherent: ~g*sqrt(K) runs for g*g
+// patches), because the first occurrence of a label always starts a run and every patch of a run shares its slot:
+// the two quadratic searches (first occurrence, rank inside the slot) touch runs, not patches.
+__global__ void __launch_bounds__(1024) sppp_slot_smem_kernel(const int64_t* __restrict__ dom,
+                                                              int32_t* __restrict__ slot,
+                                                              int32_t* __restrict__ num_slots,
+                                                              int32_t* __restrict__ counts,
+                                                              int64_t* __restrict__ slot_label,
+                                                              int32_t* __restrict__ offsets,
+                                                              int32_t* __restrict__ order, int P, int r_cap) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int Pp = (P + 3) & ~3;  // the 4-wide scan may read up to 3 entries past the last run (never taken: min(i, .))
+  long long* s_hlab = reinterpret_cast<long long*>(s_raw);  // [Pp]  label of each run
+  int* s_run = reinterpret_cast<int*>(s_hlab + Pp);         // [P]   run of each patch
+  int* s_head = s_run + P;                                  // [P+1] first patch of each run, then P
+  int* s_first = s_head + P + 1;                            // [P]   first run with the same label
+  int* s_rslot = s_first + P;                               // [P]   slot of each run
+  int* s_rrank = s_rslot + P;                               // [P]   patches of the same slot in earlier runs
+  int* s_cnt = s_rrank + P;                                 // [P]   count per slot, then exclusive offsets
+  int* s_warp = s_cnt + P;                                  // [33]  scan scratch
+  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int64_t* d = dom + (int64_t)b * P;
+  // 1. runs
+  int base = 0;
+  for (int p0 = 0; p0 < P; p0 += T) {
+    const int p = p0 + tid;
+    long long mine = 0;
+    int head = 0;
+    if (p < P) {
+      mine = d[p];
+      head = (p == 0 || d[p - 1] != mine) ? 1 : 0;
+      s_cnt[p] = 0;
+    }
+    int total;
+    const int ex = block_excl_scan(head, s_warp, &total);
+    if (p < P) {
+      const int ri = base + ex + head - 1;
+      s_run[p] = ri;
+      if (head) {
+        s_head[ri] = p;
+        s_hlab[ri] = mine;
+      }
+    }
+    base += total;
+  }
+  const int Hn = base;
+  if (tid == 0) s_head[Hn] = P;
+  if (tid < Pp - Hn && tid < 4) s_hlab[Hn + tid] = 0;
+  __syncthreads();
+  // 2. first run with the same label (16-byte shared loads; lanes of a warp read the same address: broadcast)
+  for (int i = tid; i < Hn; i += T) {
+    const long long mine = s_hlab[i];
+    int first = i;
+    for (int q = 0; q < i; q += 4) {
+      const longlong2 a = *reinterpret_cast<const longlong2*>(s_hlab + q);
+      const longlong2 c = *reinterpret_cast<const longlong2*>(s_hlab + q + 2);
+      const unsigned m = (a.x == mine ? 1u : 0u) | (a.y == mine ? 2u : 0u) | (c.x == mine ? 4u : 0u) |
+                         (c.y == mine ? 8u : 0u);
+      if (m) {
+        first = min(i, q + __ffs(m) - 1);
+        break;
+      }
+    }
+    s_first[i] = first;
+  }
+  __syncthreads();
+  // 3. leader runs (first[i] == i) take consecutive slots in patch order = the dict's insertion order
+  base = 0;
+  for (int i0 = 0; i0 < Hn; i0 += T) {
+    const int i = i0 + tid;
+    const int lead = (i < Hn && s_first[i] == i) ? 1 : 0;
+    int total;
+    const int ex = block_excl_scan(lead, s_warp, &total);
+    if (lead) {
+      const int r = base + ex;
+      s_rslot[i] = r;
+      if (r < r_cap) slot_label[(int64_t)b * r_cap + r] = s_hlab[i];
+    }
+    base += total;
+  }
+  const int R = base;
+  __syncthreads();
+  // 4. every run: its leader's slot, its share of the count, and the patches of its slot that come before it
+  for (int i = tid; i < Hn; i += T) {
+    const int f = s_first[i];
+    const int r = s_rslot[f];
+    if (f != i) s_rslot[i] = r;
+    atomicAdd(&s_cnt[r], s_head[i + 1] - s_head[i]);
+    int rank = 0;
+    for (int q = f; q < i; ++q) rank += s_first[q] == f ? s_head[q + 1] - s_head[q] : 0;
+    s_rrank[i] = rank;
+  }
+  __syncthreads();
+  // 5. counts -> offsets
+  base = 0;
+  for (int r0 = 0; r0 < R; r0 += T) {
+    const int r = r0 + tid;
+    const int c = r < R ? s_cnt[r] : 0;
+    int total;
+    const int ex = block_excl_scan(c, s_warp, &total);
+    if (r < R) {
+      s_cnt[r] = base + ex;
+      if (r <= r_cap) offsets[(int64_t)b * (r_cap + 1) + r] = base + ex;  // r == r_cap: end of the last kept row
+      if (r < r_cap) counts[(int64_t)b * r_cap + r] = c;
+    }
+    base += total;
+  }
+  __syncthreads();
+  if (tid == 0) num_slots[b] = R;
+  for (int q = R + tid; q <= r_cap; q += T) {  // unused rows: offsets = P, counts = 0
+    offsets[(int64_t)b * (r_cap + 1) + q] = P;
+    if (q < r_cap) {
+      counts[(int64_t)b * r_cap + q] = 0;
+      slot_label[(int64_t)b * r_cap + q] = 0;
+    }
+  }
+  // 6. patches: slot id and CSR position (runs of one slot are laid out in run order, patches ascending)
+  int32_t* ord = order + (int64_t)b * P;
+  for (int p = tid; p < P; p += T) {
+    const int i = s_run[p];
+    const int r = s_rslot[i];
+    slot[(int64_t)b * P + p] = r;
+    ord[s_cnt[r] + s_rrank[i] + p - s_head[i]] = p;
+  }
+}
+
+// ---- pool forward: TMA-staged tiles ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+constexpr int kSliceBytes = 128;   // bytes of one patch row per tile
+constexpr int kPoolThreads = 256;  // 16 slot lanes x 16 column groups of 8 bytes
+
+__device__ __forceinline__ int lower_bound_i32(const int* a, int lo, int hi, int key) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <typename TIn> struct Group8;  // the 8 bytes one thread owns of a tile row
+template <> struct Group8<__nv_bfloat16> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void add(const unsigned char* p, float (&acc)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    acc[0] += __uint_as_float(u.x << 16);
+    acc[1] += __uint_as_float(u.x & 0xffff0000u);
+    acc[2] += __uint_as_float(u.y << 16);
+    acc[3] += __uint_as_float(u.y & 0xffff0000u);
+  }
+};
+template <> struct Group8<float> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void add(const unsigned char* p, float (&acc)[2]) {
+    const float2 u = *reinterpret_cast<const float2*>(p);
+    acc[0] += u.x;
+    acc[1] += u.y;
+  }
+};
+template <int N> __device__ __forceinline__ void store_group(float* o, const float (&v)[N]) {
+  if constexpr (N == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  else *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+}
+template <int N> __device__ __forceinline__ void store_group(__nv_bfloat16* o, const float (&v)[N]) {
+  if constexpr (N == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  else *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v[0], v[1]);
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void lds_group(const float* p, float (&v)[N]) {
+  if constexpr (N == 4) {
+    const float4 u = *reinterpret_cast<const float4*>(p);
+    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+  } else {
+    const float2 u = *reinterpret_cast<const float2*>(p);
+    v[0] = u.x; v[1] = u.y;
+  }
+}
+template <int N> __device__ __forceinline__ void sts_group(float* p, const float (&v)[N]) {
+  if constexpr (N == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+
+// (a) P <= 256: the whole [P x 128 B] tile of an item = (image b, 128-byte column slice s) is one TMA box.
+// Persistent CTAs; a ring of `stages` boxes runs ahead across item boundaries, and the CSR of the NEXT item is
+// fetched by cp.async into the other of two buffers while this tile is summed, so nothing but the barrier wait
+// sits between two tiles.  Tensor map: x viewed as [B*P rows, D cols], box = P x (128 / sizeof(TIn)) columns.
+// Thread (lane16 = tid / 16, cg = tid % 16) sums the 8-byte column group cg over the CSR lists of slots lane16,
+// lane16 + 16, ... in ascending patch order.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kPoolThreads) sppp_pool_fwd_tma_kernel(
+    const __grid_constant__ CUtensorMap tm, const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+    const int32_t* __restrict__ num_slots, TOut* __restrict__ out, int P, int R, int D, int r_cap, int nslices,
+    int nitems, int stages) {
+  constexpr int NV = Group8<TIn>::N;
+  constexpr int CW = kSliceBytes / (int)sizeof(TIn);
+  // All shared memory is dynamic so that the TMA destination sits at the (128-byte aligned) base of the window.
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t tile_bytes = (uint32_t)P * kSliceBytes;
+  unsigned char* ring = s_raw;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + (size_t)stages * tile_bytes);  // [4]
+  int* s_order = reinterpret_cast<int*>(s_bar + 4);  // [2][P]
+  int* s_off = s_order + 2 * P;                      // [2][R+1]
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, sl = tid >> 4;
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto issue = [&](int j) {  // one thread
+    const int item = blockIdx.x + j * gridDim.x;
+    const int b = item / nslices, s = item - b * nslices;
+    const int st = j % stages;
+    const uint32_t bar = ptx::smem_u32(&s_bar[st]);
+    ptx::mbar_expect_tx(bar, tile_bytes);
+    ptx::tma_load_2d(ptx::smem_u32(ring + (size_t)st * tile_bytes), &tm, bar, s * CW, b * P);
+  };
+  auto fetch_csr = [&](int j, int buf) {  // all threads, asynchronous
+    const int b = (blockIdx.x + j * gridDim.x) / nslices;
+    int* so = s_order + buf * P;
+    int* sf = s_off + buf * (R + 1);
+    for (int i = tid; i < P; i += kPoolThreads) cp_async4(so + i, order + (int64_t)b * P + i);
+    for (int r = tid; r <= R && r <= r_cap; r += kPoolThreads) cp_async4(sf + r, offsets + (int64_t)b * (r_cap + 1) + r);
+  };
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm);
+    for (int i = 0; i < stages; ++i) ptx::mbar_init(ptx::smem_u32(&s_bar[i]), 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+    for (int j = 0; j < stages && j < my_items; ++j) issue(j);
+  }
+  fetch_csr(0, 0);
+  int ns_next = min(min(num_slots[blockIdx.x / nslices], r_cap), R);
+
+  for (int j = 0; j < my_items; ++j) {
+    const int item = blockIdx.x + j * gridDim.x;
+    const int b = item / nslices, s = item - b * nslices;
+    const int ns = ns_next;
+    const int buf = j & 1;
+    const int* so = s_order + buf * P;
+    const int* sf = s_off + buf * (R + 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();  // this item's CSR is in place (and the barriers are initialised, first time round)
+    if (j + 1 < my_items) {
+      ns_next = min(min(num_slots[(blockIdx.x + (j + 1) * gridDim.x) / nslices], r_cap), R);
+      fetch_csr(j + 1, buf ^ 1);  // that buffer's readers finished before the barrier that ended item j-1
+    }
+    const int st = j % stages;
+    ptx::mbar_wait(ptx::smem_u32(&s_bar[st]), (uint32_t)(j / stages) & 1u);
+    const unsigned char* tile = ring + (size_t)st * tile_bytes + cg * 8;
+    const int d0 = s * CW + cg * NV;
+    for (int r = sl; r < R; r += 16) {
+      const int beg = r < ns ? sf[r] : 0, end = r < ns ? sf[r + 1] : 0;
+      float acc[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) acc[e] = 0.f;
+#pragma unroll 4
+      for (int t = beg; t < end; ++t) Group8<TIn>::add(tile + (size_t)so[t] * kSliceBytes, acc);
+      if (d0 < D) {
+        const float n = (float)max(end - beg, 1);
+#pragma unroll
+        for (int e = 0; e < NV; ++e) acc[e] = acc[e] / n;
+        store_group<NV>(out + ((int64_t)b * R + r) * D + d0, acc);
+      }
+    }
+    __syncthreads();  // every thread is done with this stage and this CSR buffer
+    if (tid == 0 && j + stages < my_items) issue(j + stages);
+  }
+}
+
+// (b) P > 256: rows are streamed in CSR ORDER (slot-major, ascending patch id inside a slot), so the shared-memory
+// tile is already sorted by slot and the pooling is a segmented sum over a contiguous stream.  Per chunk of 128
+// CSR positions each thread copies 4 x 16 bytes with cp.async (3-stage ring), then
+//   phase 1: thread (lane16, cg) sums the 8-byte column group cg of positions [8*lane16, 8*lane16 + 8); a slot that
+//            begins and ends inside the lane is finished on the spot; the part of a slot that began in an earlier
+//            lane is published as the lane's HEAD; the part of a slot that goes on past the lane is its TAIL;
+//   phase 2: the thread holding the tail of a slot adds the heads of the following lanes until the slot ends (1-2
+//            for compact superpixels) and writes the mean; a slot still open at the end of the chunk is carried.
+// Every position is touched once, the work per lane is equal whatever the shape of the superpixels, and the order
+// of the additions is fixed.
+constexpr int kSortedThreads = 256;
+constexpr int kRowsPerLane = 8;
+constexpr int kSortedChunkBytes = 16 * 1024;  // per stage: 128 positions of a 128-byte slice, or 256 of a 64-byte one
+
+// SLICE = bytes of a patch row one item covers: 128, or 64 when 128 would leave SMs without an item (a CTA's rate is
+// bound by its own wait -> sum -> wait chain, so small batches want more, narrower items).
+template <typename TIn, typename TOut, int SLICE>
+__global__ void __launch_bounds__(kSortedThreads) sppp_pool_fwd_sorted_kernel(
+    const TIn* __restrict__ x, const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+    const int32_t* __restrict__ num_slots, TOut* __restrict__ out, int P, int R, int D, int r_cap, int nslices,
+    int nitems) {
+  constexpr int kSortedStages = 3;
+  constexpr int NV = Group8<TIn>::N;
+  constexpr int CW = SLICE / (int)sizeof(TIn);
+  constexpr int CGS = SLICE / 8;                      // 8-byte column groups per row
+  constexpr int kLanes = kSortedThreads / CGS;        // row lanes
+  constexpr int kChunkPos = kLanes * kRowsPerLane;    // CSR positions per chunk
+  constexpr int PIECES = SLICE / 16;                  // 16-byte copies per row
+  constexpr int kCopyRows = kSortedThreads / PIECES;  // rows per copy pass
+  constexpr uint32_t kChunkBytes = kChunkPos * SLICE;
+  static_assert(kChunkBytes == kSortedChunkBytes, "stage size");
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  unsigned char* ring = s_raw;                                                         // [3][128][128 B]
+  float* s_head = reinterpret_cast<float*>(ring + kSortedStages * kChunkBytes);        // [kLanes][CGS][NV]
+  float* s_carry = s_head + kLanes * CGS * NV;                                              // [2][16][NV]
+  int* s_cont = reinterpret_cast<int*>(s_carry + 2 * CGS * NV);                        // [kLanes] head goes on past its lane
+  int* s_off = s_cont + kLanes;                                                            // [R+1]
+  int* s_order = s_off + (R + 1);                                                      // [P]
+  short* s_lslot = reinterpret_cast<short*>(s_order + P);                              // [P/8 + 1] slot holding position 8*i
+  const int tid = threadIdx.x;
+  const int cg = tid % CGS, sl = tid / CGS;
+  const int crow = tid / PIECES, cpiece = tid % PIECES;  // copy role: position crow (+kCopyRows per pass), piece cpiece
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int b = item / nslices, s = item - b * nslices;
+    const int ns = min(min(num_slots[b], r_cap), R);
+    __syncthreads();  // the previous item's readers are done with the CSR buffers
+    for (int i = tid; i < P; i += kSortedThreads) cp_async4(s_order + i, order + (int64_t)b * P + i);
+    for (int r = tid; r <= ns; r += kSortedThreads) cp_async4(s_off + r, offsets + (int64_t)b * (r_cap + 1) + r);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int covered = s_off[ns];  // positions [0, covered) belong to slots [0, ns)
+    const int nchunks = (covered + kChunkPos - 1) / kChunkPos;
+    for (int i = tid; i * kRowsPerLane < covered; i += kSortedThreads) {
+      const int t = i * kRowsPerLane;
+      int lo = 0, hi = ns;  // last r with s_off[r] <= t
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= t) lo = mid;
+        else hi = mid;
+      }
+      s_lslot[i] = (short)lo;
+    }
+    const int d0 = s * CW + cg * NV;
+    // slots without patches (or beyond r_cap) pool to zero
+    for (int r = sl; r < R; r += kLanes) {
+      if ((r >= ns || s_off[r + 1] == s_off[r]) && d0 < D) {
+        float z[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) z[e] = 0.f;
+        store_group<NV>(out + ((int64_t)b * R + r) * D + d0, z);
+      }
+    }
+    // copy role: 16-byte piece `cpiece` of positions crow, crow + 32, ...; positions past `covered` re-read the last
+    // row (never summed), so the loop carries no predicate; 32-bit row offsets (the host checked P*D*size < 2^31)
+    const unsigned char* xs = reinterpret_cast<const unsigned char*>(x) +
+                              ((int64_t)b * P * D + (int64_t)s * CW) * sizeof(TIn) + cpiece * 16;
+    const bool piece_ok = (int64_t)s * SLICE + cpiece * 16 < (int64_t)D * (int64_t)sizeof(TIn);
+    const uint32_t pitch = (uint32_t)D * (uint32_t)sizeof(TIn);
+    const uint32_t dst0 = ptx::smem_u32(ring) + crow * SLICE + cpiece * 16;
+    auto copy_chunk = [&](int c) {  // all threads
+      if (c < nchunks && piece_ok) {
+        const uint32_t dst = dst0 + (uint32_t)(c % kSortedStages) * kChunkBytes;
+        const int t0 = c * kChunkPos + crow;
+#pragma unroll
+        for (int q = 0; q < kChunkPos / kCopyRows; ++q) {
+          const int t = min(t0 + kCopyRows * q, covered - 1);
+          const unsigned char* src = xs + (uint32_t)s_order[t] * pitch;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * kCopyRows * SLICE), "l"(src) : "memory");
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int c = 0; c < kSortedStages - 1; ++c) copy_chunk(c);
+    int carry_buf = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      copy_chunk(c + kSortedStages - 1);  // its stage was released by the barrier that closed chunk c-1
+      cp_async_wait<kSortedStages - 1>();
+      __syncthreads();  // chunk c is in shared memory; phase 2 of chunk c-1 is over (s_head / s_cont are free)
+      const unsigned char* tile = ring + (size_t)(c % kSortedStages) * kChunkBytes + cg * 8;
+      // ---- phase 1
+      const int a = c * kChunkPos + sl * kRowsPerLane;  // first position of this lane
+      const int lane_end = min(a + kRowsPerLane, covered);
+      float acc[NV], tail[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) acc[e] = 0.f;
+      int tail_slot = -1;       // slot whose sum continues past this lane (this thread then owns its completion)
+      bool is_head = false;     // the run being summed began before this lane
+      if (a < covered) {
+        int r = s_lslot[a / kRowsPerLane];
+        int nxt = s_off[r + 1];
+        is_head = s_off[r] < a;
+#pragma unroll
+        for (int i = 0; i < kRowsPerLane; ++i) {
+          const int t = a + i;
+          if (t < lane_end) {
+            if (t >= nxt) {  // slot r ended at t: finish or publish it, move to the slot holding t
+              if (is_head) {
+                sts_group<NV>(s_head + (sl * CGS + cg) * NV, acc);
+                if (cg == 0) s_cont[sl] = 0;
+                is_head = false;
+              } else if (d0 < D) {
+                const float n = (float)(nxt - s_off[r]);
+                float v[NV];
+#pragma unroll
+                for (int e = 0; e < NV; ++e) v[e] = acc[e] / n;
+                store_group<NV>(out + ((int64_t)b * R + r) * D + d0, v);
+              }
+#pragma unroll
+              for (int e = 0; e < NV; ++e) acc[e] = 0.f;
+              do {
+                ++r;
+                nxt = s_off[r + 1];
+              } while (t >= nxt);  // skips empty slots
+            }
+            Group8<TIn>::add(tile + (size_t)(sl * kRowsPerLane + i) * SLICE, acc);
+          }
+        }
+        // the run open at the end of the lane
+        const bool goes_on = nxt > lane_end;  // more positions of slot r follow (next lane or next chunk)
+        if (is_head) {
+          sts_group<NV>(s_head + (sl * CGS + cg) * NV, acc);
+          if (cg == 0) s_cont[sl] = goes_on ? 1 : 0;
+        } else if (goes_on) {
+          tail_slot = r;
+#pragma unroll
+          for (int e = 0; e < NV; ++e) tail[e] = acc[e];
+        } else if (d0 < D) {
+          const float n = (float)(nxt - s_off[r]);
+          float v[NV];
+#pragma unroll
+          for (int e = 0; e < NV; ++e) v[e] = acc[e] / n;
+          store_group<NV>(out + ((int64_t)b * R + r) * D + d0, v);
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: owners complete their slots.  Lane 0 also owns the slot carried in from the previous chunk.
+      auto complete = [&](int r, float (&sum)[NV], int l2) {
+        for (; l2 < kLanes; ++l2) {
+          if (c * kChunkPos + l2 * kRowsPerLane >= covered) break;  // cannot happen for an open slot; safety
+          float v[NV];
+          lds_group<NV>(s_head + (l2 * CGS + cg) * NV, v);
+#pragma unroll
+          for (int e = 0; e < NV; ++e) sum[e] += v[e];
+          if (!s_cont[l2]) {
+            if (d0 < D) {
+              const float n = (float)(s_off[r + 1] - s_off[r]);
+#pragma unroll
+              for (int e = 0; e < NV; ++e) sum[e] = sum[e] / n;
+              store_group<NV>(out + ((int64_t)b * R + r) * D + d0, sum);
+            }
+            return;
+          }
+        }
+        sts_group<NV>(s_carry + ((carry_buf ^ 1) * CGS + cg) * NV, sum);  // still open: carry into the next chunk
+      };
+      if (sl == 0 && c > 0) {
+        const int a0 = c * kChunkPos;
+        const int r0 = s_lslot[a0 / kRowsPerLane];
+        if (s_off[r0] < a0) {  // the first slot of this chunk began in an earlier chunk
+          float sum[NV];
+          lds_group<NV>(s_carry + (carry_buf * CGS + cg) * NV, sum);
+          complete(r0, sum, 0);
+        }
+      }
+      if (tail_slot >= 0) complete(tail_slot, tail, sl + 1);
+      carry_buf ^= 1;
+    }
+    cp_async_wait<0>();
+  }
+}
+
+// ---- pool backward: pre-divided gradient rows in shared memory, 16-byte stores ----------------------------
+constexpr int kBwdCols = 64;
+constexpr int kBwdThreads = 128;  // small CTAs: the whole grid is resident at once, prologue latencies overlap
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kBwdThreads) sppp_pool_bwd_tile_kernel(const TIn* __restrict__ dout,
+                                                                         const int32_t* __restrict__ slot,
+                                                                         const int32_t* __restrict__ counts,
+                                                                         TOut* __restrict__ dx, int P, int R, int D,
+                                                                         int r_cap, int nslices) {
+  constexpr int NVO = 16 / (int)sizeof(TOut);  // columns per 16-byte store
+  constexpr int TPR = kBwdCols / NVO;          // threads per patch row
+  constexpr int ROWS = kBwdThreads / TPR;
+  extern __shared__ __align__(16) float s_g[];  // [R][64] gradient rows / count, then [P] slot ids
+  int* s_slot = reinterpret_cast<int*>(s_g + (size_t)R * kBwdCols);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / nslices, s = blockIdx.x - b * nslices;
+  const int col0 = s * kBwdCols;
+  for (int i = tid; i < P; i += kBwdThreads) {
+    const int r = slot[(int64_t)b * P + i];
+    s_slot[i] = (r >= 0 && r < R && r < r_cap) ? r : -1;
+  }
+  for (int i = tid; i < R * kBwdCols; i += kBwdThreads) {
+    const int r = i / kBwdCols, c = col0 + (i % kBwdCols);
+    float v = 0.f;
+    if (c < D && r < r_cap)
+      v = Elem<TIn>::ld(dout + ((int64_t)b * R + r) * D + c) / (float)max(counts[(int64_t)b * r_cap + r], 1);
+    s_g[i] = v;
+  }
+  __syncthreads();
+  const int cgo = tid % TPR, rl = tid / TPR;
+  const int c = col0 + cgo * NVO;
+  if (c >= D) return;
+  TOut* o = dx + (int64_t)b * P * D + c;
+#pragma unroll 4
+  for (int p = rl; p < P; p += ROWS) {
+    const int r = s_slot[p];
+    float f[NVO];
+    if (r >= 0) {
+      const float4* g = reinterpret_cast<const float4*>(s_g + r * kBwdCols + cgo * NVO);
+#pragma unroll
+      for (int e = 0; e < NVO / 4; ++e) {
+        const float4 v = g[e];
+        f[4 * e] = v.x; f[4 * e + 1] = v.y; f[4 * e + 2] = v.z; f[4 * e + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NVO; ++e) f[e] = 0.f;
+    }
+    if constexpr (NVO == 8) {
+      store8(o + (int64_t)p * D, f);
+    } else {
+      *reinterpret_cast<float4*>(o + (int64_t)p * D) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+// Tiled path when the rows can be described to TMA (16-byte aligned base and row pitch) and the tile ring fits.
 template <typename TIn, typename TOut>
 int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets, const int32_t* num_slots,
                     void* out, int B, int P, int R, int D, int r_cap, cudaStream_t st) {
+  constexpr int CW = kSliceBytes / (int)sizeof(TIn);
+  constexpr int NV = Group8<TIn>::N;
+  const int nslices = ceil_div(D, CW);
+  const int nitems = B * nslices;
+  const bool aligned = ((uintptr_t)x % 16 == 0) && (((size_t)D * sizeof(TIn)) % 16 == 0) &&
+                       ((uintptr_t)out % 16 == 0) && (D % 4 == 0) && R < 32768 && (int64_t)B * P < INT_MAX &&
+                       (int64_t)B * nslices < INT_MAX;
+  if (aligned && P <= 256 && encode_fn() != nullptr) {  // (a) one TMA box per item
+    const size_t tile_bytes = (size_t)P * kSliceBytes;
+    const int stages = tile_bytes > 12 * 1024 ? 2 : 4;
+    const size_t smem = stages * tile_bytes + 32 + 2 * ((size_t)P + R + 1) * 4;
+    if (smem <= 200 * 1024) {
+      CUtensorMap tm;
+      cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)B * P};
+      cuuint64_t gstr[1] = {(cuuint64_t)D * sizeof(TIn)};
+      cuuint32_t box[2] = {(cuuint32_t)CW, (cuuint32_t)P};
+      cuuint32_t estr[2] = {1, 1};
+      const CUresult r = encode_fn()(
+          &tm, sizeof(TIn) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+          const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("sppp_pool_fwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return FAVIT_ERR_CUDA;
+      }
+      static bool configured = false;  // per instantiation
+      if (!configured) {
+        FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_fwd_tma_kernel<TIn, TOut>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      int per_sm = (int)((220 * 1024) / (smem + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+      const int grid = nitems < num_sms() * per_sm ? nitems : num_sms() * per_sm;
+      sppp_pool_fwd_tma_kernel<TIn, TOut><<<grid, kPoolThreads, smem, st>>>(
+          tm, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, nslices, nitems, stages);
+      FAVIT_CHECK_LAUNCH();
+      return FAVIT_OK;
+    }
+  }
+  if (aligned && P > 256 && (int64_t)P * D * (int64_t)sizeof(TIn) < INT_MAX) {  // (b) rows streamed in CSR order
+    const bool narrow = nitems < 2 * num_sms();  // 64-byte slices: twice the items
+    const int slice = narrow ? 64 : 128;
+    const int lanes = kSortedThreads / (slice / 8);
+    const size_t smem = (size_t)3 * kSortedChunkBytes + (size_t)(lanes + 2) * (slice / 8) * NV * 4 + lanes * 4 +
+                        ((size_t)R + 1 + P) * 4 + ((size_t)P / kRowsPerLane + 2) * 2;
+    if (smem <= 200 * 1024) {
+      static bool configured = false;  // per instantiation
+      if (!configured) {
+        FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_fwd_sorted_kernel<TIn, TOut, 128>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_fwd_sorted_kernel<TIn, TOut, 64>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      int per_sm = (int)((220 * 1024) / (smem + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+      const int sl_items = B * ceil_div(D * (int)sizeof(TIn), slice);
+      const int grid = sl_items < num_sms() * per_sm ? sl_items : num_sms() * per_sm;
+      if (narrow)
+        sppp_pool_fwd_sorted_kernel<TIn, TOut, 64><<<grid, kSortedThreads, smem, st>>>(
+            (const TIn*)x, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, sl_items / B, sl_items);
+      else
+        sppp_pool_fwd_sorted_kernel<TIn, TOut, 128><<<grid, kSortedThreads, smem, st>>>(
+            (const TIn*)x, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, sl_items / B, sl_items);
+      FAVIT_CHECK_LAUNCH();
+      return FAVIT_OK;
+    }
+  }
   const bool vec = (D % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
   const int per = vec ? 256 : 32;
   const int64_t items = (int64_t)B * R * ceil_div(D, per);
@@ -287,6 +1014,21 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
 template <typename TIn, typename TOut>
 int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts, void* dx, int B, int P, int R,
                     int D, int r_cap, cudaStream_t st) {
+  const size_t smem = (size_t)R * kBwdCols * sizeof(float) + (size_t)P * 4;
+  const int nslices = ceil_div(D, kBwdCols);
+  if (((uintptr_t)dx % 16 == 0) && (((size_t)D * sizeof(TOut)) % 16 == 0) && smem <= 160 * 1024 &&
+      (int64_t)B * nslices < INT_MAX) {
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+      FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_bwd_tile_kernel<TIn, TOut>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
+    sppp_pool_bwd_tile_kernel<TIn, TOut><<<(unsigned)(B * nslices), kBwdThreads, smem, st>>>(
+        (const TIn*)dout, slot, counts, (TOut*)dx, P, R, D, r_cap, nslices);
+    FAVIT_CHECK_LAUNCH();
+    return FAVIT_OK;
+  }
   const bool vec = (D % 8 == 0) && ((uintptr_t)dout % 16 == 0) && ((uintptr_t)dx % 16 == 0);
   const int per = vec ? 256 : 32;
   const int64_t items = (int64_t)B * P * ceil_div(D, per);
@@ -323,20 +1065,41 @@ extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int im
   const int P = grid * grid;
   const int ppl = ceil_div(patch * patch, 32);
   const unsigned blocks = (unsigned)ceil_div64((int64_t)B * P, 8);
+  const bool vec = (img_w % 2 == 0) && ((uintptr_t)labels % 16 == 0);
+  if (vec && patch == 16) {
+    sppp_dominant_vec_kernel<16><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+  } else if (vec && patch == 8) {
+    sppp_dominant_vec_kernel<8><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+  } else if (vec && patch == 32) {
+    sppp_dominant_vec_kernel<32><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+  } else {
 #define FAVIT_DOM(PPL)                                                                                   \
   sppp_dominant_kernel<PPL><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, patch, grid)
-  if (ppl <= 1) FAVIT_DOM(1);
-  else if (ppl <= 2) FAVIT_DOM(2);
-  else if (ppl <= 4) FAVIT_DOM(4);
-  else if (ppl <= 8) FAVIT_DOM(8);
-  else if (ppl <= 16) FAVIT_DOM(16);
-  else FAVIT_DOM(32);
+    if (ppl <= 1) FAVIT_DOM(1);
+    else if (ppl <= 2) FAVIT_DOM(2);
+    else if (ppl <= 4) FAVIT_DOM(4);
+    else if (ppl <= 8) FAVIT_DOM(8);
+    else if (ppl <= 16) FAVIT_DOM(16);
+    else FAVIT_DOM(32);
 #undef FAVIT_DOM
+  }
   FAVIT_CHECK_LAUNCH();
-  if (P <= 1024)
+  const size_t slot_smem = (size_t)((P + 3) & ~3) * 8 + (size_t)P * 24 + 34 * 4;
+  if (slot_smem <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_slot_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            200 * 1024));
+      configured = true;
+    }
+    const int threads = P >= 1024 ? 1024 : ((P + 31) / 32) * 32;
+    sppp_slot_smem_kernel<<<B, threads, slot_smem, st>>>(dom, slot, num_slots, counts, slot_label, offsets, order,
+                                                        P, r_cap);
+  } else if (P <= 1024) {
     sppp_slot_kernel<256><<<B, 256, 0, st>>>(dom, slot, num_slots, counts, slot_label, offsets, order, P, r_cap);
-  else
+  } else {
     sppp_slot_kernel<1024><<<B, 1024, 0, st>>>(dom, slot, num_slots, counts, slot_label, offsets, order, P, r_cap);
+  }
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }

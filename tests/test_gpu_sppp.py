@@ -45,7 +45,8 @@ def test_assign_and_pool_match_reference_fixtures():
             assert torch.equal(pooled2, pooled)
 
 
-@pytest.mark.parametrize("S,ps,K,B", [(32, 4, 4, 5), (224, 16, 16, 8), (224, 4, 16, 2), (512, 8, 64, 2), (96, 32, 9, 3)])
+@pytest.mark.parametrize("S,ps,K,B", [(32, 4, 4, 5), (224, 16, 16, 8), (224, 4, 16, 2), (512, 8, 64, 2), (96, 32, 9, 3),
+                                      (512, 8, 256, 2), (64, 8, 4, 3), (224, 14, 16, 2)])
 def test_assign_bit_exact_vs_oracle(S, ps, K, B):
     from favit_b200.synth import voronoi_label_maps
     lm = voronoi_label_maps(B, S, K, seed=S + ps, device="cpu").numpy()
@@ -62,6 +63,49 @@ def test_assign_bit_exact_vs_oracle(S, ps, K, B):
         assert np.array_equal(a.order[b].cpu().numpy(), ref["order"][b])
 
 
+@pytest.mark.parametrize("ps,S", [(8, 48), (16, 64), (32, 64), (16, 50)])
+def test_assign_vector_path_adversarial(ps, S):
+    """The 16-byte-load dominant kernel (patch 8/16/32, even width) and the shared-memory slot kernel on maps built to
+    break them: pixel-level noise from a small alphabet (ties in almost every patch, ids that are negative, huge, or
+    first seen in non-sorted order), every pixel distinct (as many slots as patches), and one label everywhere."""
+    rng = np.random.default_rng(ps + S)
+    alphabet = np.asarray([9, -7, 0, 3, 2 ** 40, 11, 5, -2 ** 50], dtype=np.int64)
+    noisy = alphabet[rng.integers(0, len(alphabet), size=(3, S, S))]
+    two = np.where(rng.random((2, S, S)) < 0.5, 4, 1).astype(np.int64)         # near-ties between two labels
+    g = S // ps
+    blocks = rng.permutation(g * g).astype(np.int64).reshape(g, g)              # one distinct label per patch
+    per_patch = np.kron(blocks, np.ones((ps, ps), dtype=np.int64))
+    per_patch = np.pad(per_patch, ((0, S - g * ps), (0, S - g * ps)))[None]
+    const = np.full((1, S, S), 17, dtype=np.int64)
+    half = np.zeros((1, S, S), dtype=np.int64)
+    half[:, :, 1::2] = -3                                                      # exact half/half tie in every patch
+    for lm in (noisy, two, per_patch, const, half):
+        ref = oracle.assign_oracle(lm, ps, S)
+        a = _assign(lm, ps, S)
+        assert np.array_equal(a.dom.cpu().numpy(), ref["dom"])
+        assert np.array_equal(a.slot.cpu().numpy(), ref["slot"])
+        assert np.array_equal(a.num_slots.cpu().numpy(), ref["num_slots"])
+        for b in range(lm.shape[0]):
+            R = int(ref["num_slots"][b])
+            assert np.array_equal(a.counts[b, :R].cpu().numpy(), ref["counts"][b])
+            assert np.array_equal(a.slot_label[b, :R].cpu().numpy(), ref["slot_label"][b])
+            assert np.array_equal(a.offsets[b, :R + 1].cpu().numpy(), ref["offsets"][b])
+            assert np.array_equal(a.order[b].cpu().numpy(), ref["order"][b])
+
+
+def test_assign_r_cap_smaller_than_slots():
+    """More slots than r_cap: num_slots reports the true R, the first r_cap rows are still exact."""
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(2, 128, 16, seed=5, device="cpu").numpy()
+    ref = oracle.assign_oracle(lm, 8, 128)
+    a = _assign(lm, 8, 128, r_cap=5)
+    assert np.array_equal(a.num_slots.cpu().numpy(), ref["num_slots"])
+    assert np.array_equal(a.slot.cpu().numpy(), ref["slot"])
+    for b in range(2):
+        assert np.array_equal(a.counts[b].cpu().numpy(), ref["counts"][b][:5])
+        assert np.array_equal(a.offsets[b].cpu().numpy(), ref["offsets"][b][:6])
+
+
 def test_assign_adversarial_maps():
     rng = np.random.default_rng(3)
     # random labels per pixel from a small alphabet: many ties, negative and huge ids
@@ -75,7 +119,9 @@ def test_assign_adversarial_maps():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-@pytest.mark.parametrize("B,S,ps,K,D", [(4, 32, 4, 4, 24), (8, 224, 16, 16, 384), (2, 128, 8, 16, 100)])
+@pytest.mark.parametrize("B,S,ps,K,D", [(4, 32, 4, 4, 24), (8, 224, 16, 16, 384), (2, 128, 8, 16, 100),
+                                        (2, 512, 8, 64, 384), (3, 512, 8, 256, 192), (2, 224, 4, 16, 72),
+                                        (5, 64, 8, 4, 7), (2, 256, 16, 16, 776)])
 def test_pool_fwd_bwd_vs_oracle(B, S, ps, K, D, dtype):
     from favit_b200 import ops
     from favit_b200.synth import voronoi_label_maps

@@ -1,7 +1,8 @@
 """Per-kernel microbenchmark at the shapes of a workload (default: ViT-B/16, 256 images -> M = 50432 tokens).
 CUDA-event timing, inputs cycled through several buffers so that nothing stays L2-resident between iterations.
 
-    python tools/kernel_bench.py [--M 50432] [--D 768] [--H 12] [--N 197] [--iters 20] [--only gemm|ln|attn]
+    python tools/kernel_bench.py [--B 256] [--D 768] [--H 12] [--N 197] [--iters 20] [--only gemm|ln|attn|sppp]
+    python tools/kernel_bench.py --only sppp --S 224 --ps 16 --K 16 --D 384      # SPPP ViT-S (BASELINE configs[1])
 """
 import argparse
 import json
@@ -35,6 +36,32 @@ def timeit(fn, iters, nbuf):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
+def timeit_graph(fn, iters, nbuf):
+    """Same, with the `iters` launches captured in one CUDA graph: no host launch cost between kernels, which is what
+    a 10-us kernel needs (an eager loop measures the Python/ctypes call rate instead)."""
+    for i in range(2):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(iters):
+                keep.append(fn(i % nbuf))
+    best = None
+    for _ in range(5):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / iters * 1e3
+        best = t if best is None else min(best, t)
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=256)
@@ -44,6 +71,10 @@ def main():
     ap.add_argument("--W", type=int, default=7)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--S", type=int, default=224, help="sppp: image size")
+    ap.add_argument("--ps", type=int, default=16, help="sppp: patch size")
+    ap.add_argument("--K", type=int, default=16, help="sppp: superpixels per image")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     B, N, D, H = a.B, a.N, a.D, a.H
     M = B * N
@@ -113,8 +144,29 @@ def main():
         o, lse = raw.attn_fwd(qkv[0], B, N, H, hd, a.W)
         rec("attn bwd", timeit(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, hd, a.W)[0], a.iters, nbuf), None,
             8.0 * M * D * 2)
+    if a.only in ("", "sppp"):
+        from favit_b200 import ops
+        from favit_b200.synth import voronoi_label_maps
+        S, ps, K = a.S, a.ps, a.K
+        P = (S // ps) ** 2
+        Ds = a.D if a.only == "sppp" else 384
+        nbuf = 8 if B <= 256 else 3  # 8 x 38.5 MB of embeddings at the ViT-S shape: nothing survives in the 126 MB L2 between launches
+        rnd = lambda *s: [torch.randn(*s, device=dev).to(bf) for _ in range(nbuf)]
+        rndf = lambda *s: [torch.randn(*s, device=dev) for _ in range(nbuf)]
+        lms = [voronoi_label_maps(B, S, K, seed=7 + i, device=dev, exact_k=True, patch_size=ps) for i in range(nbuf)]
+        asg = [ops.sppp_assign(lm, ps, S, K) for lm in lms]
+        rec(f"sppp assign  B{B} {S}px ps{ps} K{K}", timeit_graph(lambda i: ops.sppp_assign(lms[i], ps, S, K), a.iters, nbuf), None,
+            B * S * S * 8.0 + 2.0 * B * P * 4 + B * K * 4)
+        x = rnd(B, P, Ds)
+        g = rndf(B, K, Ds)
+        fwd = lambda i: ops.sppp_pool_fwd(x[i], asg[i][6], asg[i][5], asg[i][2], K, torch.float32)
+        rec(f"sppp pool fwd B{B} P{P} R{K} D{Ds} bf16->f32", timeit_graph(fwd, a.iters, nbuf), None,
+            B * P * Ds * 2.0 + B * P * 4 + B * K * Ds * 4.0 + B * K * 4)
+        bwd = lambda i: ops.sppp_pool_bwd(g[i], asg[i][1], asg[i][3], bf)
+        rec(f"sppp pool bwd B{B} P{P} R{K} D{Ds} f32->bf16", timeit_graph(bwd, a.iters, nbuf), None,
+            B * K * Ds * 4.0 + B * P * 4 + B * P * Ds * 2.0)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)
+    json.dump(rows, open(f"gpurun_out/kernel_bench{a.tag}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
