@@ -9,6 +9,12 @@ namespace favit {
 namespace attn {
 
 
+// log2 of the window multiplicities 0..16 (windows up to 15 on the tensor-core paths); [0] = -inf
+__constant__ float kLog2Int[17] = {-__builtin_huge_valf(), 0.f, 1.f, 1.5849625007211562f, 2.f, 2.321928094887362f,
+                                   2.584962500721156f, 2.807354922057604f, 3.f, 3.169925001442312f,
+                                   3.321928094887362f, 3.4594316186372978f, 3.584962500721156f, 3.700439718141092f,
+                                   3.807354922057604f, 3.9068905956085187f, 4.f};
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -134,6 +140,35 @@ __device__ __forceinline__ void store_rows(const uint8_t* tile, int lane, F dst_
   }
 }
 
+// accumulators [HD/8][4] * m -> bf16, written to global straight from the fragments: this thread holds rows lane/4 (p0)
+// and lane/4 + 8 (p1), columns nd*8 + (lane%4)*2 + {0,1}; a quad writes 16 contiguous bytes and two n-steps complete a
+// 32-byte sector in L2.  With colsum != nullptr the column sums of the values as stored are added to colsum[0..HD).
+template <int HD>
+__device__ __forceinline__ void store_frag(const float (&acc)[HD / 8][4], float m, __nv_bfloat16* p0, __nv_bfloat16* p1,
+                                           bool ok0, bool ok1, float* colsum, int lane) {
+  const int sub = (lane & 3) * 2;
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; ++nd) {
+    const uint32_t v0 = pack_bf16x2(acc[nd][0] * m, acc[nd][1] * m);
+    const uint32_t v1 = pack_bf16x2(acc[nd][2] * m, acc[nd][3] * m);
+    if (ok0) *reinterpret_cast<uint32_t*>(p0 + nd * 8 + sub) = v0;
+    if (ok1) *reinterpret_cast<uint32_t*>(p1 + nd * 8 + sub) = v1;
+    if (colsum) {
+      float c0 = (ok0 ? __uint_as_float(v0 << 16) : 0.f) + (ok1 ? __uint_as_float(v1 << 16) : 0.f);
+      float c1 = (ok0 ? __uint_as_float(v0 & 0xffff0000u) : 0.f) + (ok1 ? __uint_as_float(v1 & 0xffff0000u) : 0.f);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      }
+      if (lane < 4) {
+        atomicAdd(colsum + nd * 8 + sub, c0);
+        atomicAdd(colsum + nd * 8 + sub + 1, c1);
+      }
+    }
+  }
+}
+
 // column sums of a staged 16-row tile (rows past the end of the sequence hold exact zeros) added to dst[0..HD)
 template <int HD>
 __device__ __forceinline__ void tile_colsum(const uint8_t* tile, int lane, float* dst) {
@@ -189,8 +224,8 @@ __device__ __forceinline__ RowSlots row_slots(const KeySlots& k, int i, int N, i
   if (r.tgt >= k.lo && r.tgt <= hi) o.ts = r.tgt - k.lo;
   else o.ts = (r.tgt == N - 1) ? (k.exA ? k.nband : -1) : (k.exB ? k.nband + 1 : -1);
   if (r.pad == 0) o.ts = -1;
-  o.lb_in = log2f((float)(1 + r.pad));
-  o.lb_out = r.pad > 0 ? log2f((float)r.pad) : -CUDART_INF_F;
+  o.lb_in = kLog2Int[1 + r.pad];
+  o.lb_out = kLog2Int[r.pad];
   return o;
 }
 

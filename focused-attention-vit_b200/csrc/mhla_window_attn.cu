@@ -18,6 +18,14 @@
 
 namespace favit {
 
+// whole-sequence TMA path (mhla_window_attn_seq.cu): head_dim 64, N <= 400
+bool attn_seq_applicable(int hd, int window, int N, favit_dtype dtype, const uint8_t* mask, const void* q, const void* k,
+                         const void* v, int64_t sb, int64_t sn, int64_t shh);
+int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
+                 float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
+                 void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
+                 int64_t shh, cudaStream_t st);
 // tensor-core tile path (mhla_window_attn_mma.cu)
 bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* mask);
 int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
@@ -373,6 +381,8 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse, "mhla_attn_fwd: null out/lse");
+  if (attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) && ((uintptr_t)out % 16) == 0)
+    return attn_seq_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
   if (attn_mma_applicable(hd, window, dtype, mask))
     return attn_mma_fwd(q, k, v, out, lse, B, H, N, hd, window, scale, stride_b, stride_n, stride_h,
                         (cudaStream_t)stream);
@@ -397,6 +407,11 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse && dout && dq && dk && dv && delta, "mhla_attn_bwd: null pointer");
+  if (attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
+      ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
+      ((uintptr_t)dv % 16) == 0)
+    return attn_seq_bwd(q, k, v, out, lse, dout, dq, dk, dv, dqkv_colsum, B, H, N, window, scale, stride_b, stride_n,
+                        stride_h, (cudaStream_t)stream);
   if (attn_mma_applicable(hd, window, dtype, mask))
     return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, dqkv_colsum, B, H, N, hd, window, scale, stride_b,
                         stride_n, stride_h, (cudaStream_t)stream);

@@ -244,8 +244,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_mma_dkv_kernel(
       const WindowRow w = window_row(max(i, 0), N, sh.W);
       // unused slots carry L = +inf (P = 0); keys past the end of the sequence are never stored
       const float L = sL[slot], dl = sD[slot];
-      const float lb_in = log2f((float)(1 + w.pad));
-      const float lb_out = w.pad > 0 ? log2f((float)w.pad) : -CUDART_INF_F;
+      const float lb_in = kLog2Int[1 + w.pad], lb_out = kLog2Int[w.pad];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int e = half * 2 + c;

@@ -1,0 +1,494 @@
+// MHLA windowed attention, whole-sequence tiles (bf16, head_dim 64, no mask, window <= 15, N <= 400), sm_100a.
+//
+// Same math and reference span as mhla_window_attn.cu (/root/reference/models/mhla.py:109-154: banded softmax with the
+// duplicated-edge multiplicities of mhla.py:72-79) and the same mma.sync tile arithmetic as mhla_window_attn_mma.cu.
+// What changes is who moves the bytes.  There, every warp copies its own 16 queries + 32 key/value rows with per-lane
+// cp.async (5x read amplification out of L2, ~500 address instructions per tile, one exposed latency per warp).  Here a
+// CTA owns G whole (image, head) sequences: one thread issues a TMA box per operand ([N x 64] bf16 out of the packed
+// qkv tensor, SWIZZLE_128B, which is exactly the ldmatrix-conflict-free layout the tiles use), every row is fetched
+// once, and the warps (one per 16-row tile) read their band rows and the two edge rows (key N-1 / key 0) in place
+// through a per-lane slot -> row map.  Two CTAs per SM overlap one CTA's loads with the other's arithmetic.
+// Backward is ONE kernel: a query-major phase (delta, dQ) and a key-major phase (dK, dV) over the same four resident
+// tiles (Q, K, V, dO), so Q/K/V/dO are read once instead of twice and delta never goes through global memory.
+// The op is HBM-bound (AI = W/2 FLOP/B): algorithmic bytes fwd = 4*B*N*D*2, bwd = 8*B*N*D*2.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "attn_mma_common.cuh"
+#include "tcgen05_ptx.cuh"
+
+namespace favit {
+namespace {
+
+using namespace attn;
+
+constexpr int HD = 64;
+constexpr int kRowBytes = HD * 2;
+constexpr int kMaxThreads = 832;  // 26 tiles; keeps 78 registers per thread available at two CTAs of 13 warps per SM
+
+struct SeqParams {
+  Shape sh;
+  int G;           // (image, head) sequences per CTA
+  int alloc_rows;  // rows of one shared-memory tile: tiles * 16
+  int rows_box;    // rows per TMA box (multiple of 8, <= 256)
+  int nbox;        // boxes per operand
+  int64_t pairs;   // B * H
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a 128-byte-row tile with the 128B swizzle (base 1024-aligned)
+__device__ __forceinline__ uint32_t row_off(int row, int chunk) { return (uint32_t)((row * 8 + (chunk ^ (row & 7))) * 16); }
+
+// acc[NT][4] = A(own 16-row tile) . B^T where B row of slot s is sequence row brow[.] (per-lane, see load_b)
+template <int NT>
+__device__ __forceinline__ void scores_rows(const uint8_t* sA_tile, const uint8_t* sB, const int (&brow)[NT / 2], int lane,
+                                            float (&acc)[NT][4]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  const uint32_t bbase = smem_u32(sB);
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    load_a<HD>(sA_tile, ks, lane, a);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4(bbase + row_off(brow[np], 2 * ks + ((lane >> 3) & 1)), b);
+      mma_bf16(acc[2 * np], a, b[0], b[1]);
+      mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+// acc[8][4] += P(16 x 8NT, accumulator fragments) . rows, where the row of slot s is sequence row rrow[.] (see load_bt)
+template <int NT>
+__device__ __forceinline__ void pv_rows(const float (&p)[NT][4], const uint8_t* sRows, const int (&rrow)[NT / 2], int lane,
+                                        float (&acc)[HD / 8][4]) {
+  const uint32_t rbase = smem_u32(sRows);
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+    a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+    a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int nd = 0; nd < HD / 8; nd += 2) {
+      uint32_t b[4];
+      ldsm_x4_trans(rbase + row_off(rrow[kk], nd + (lane >> 4)), b);
+      mma_bf16(acc[nd], a, b[0], b[1]);
+      mma_bf16(acc[nd + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// One thread: barrier init + every TMA box of the CTA's sequences.  NOPS operand tiles per sequence.
+template <int NOPS>
+__device__ __forceinline__ void issue_loads(const CUtensorMap* const (&tm)[NOPS], uint8_t* tiles, size_t pair_bytes,
+                                            size_t tile_bytes, uint32_t bar, const SeqParams& p, int64_t pair0) {
+  ptx::mbar_init(bar, 1);
+  ptx::fence_barrier_init();
+  ptx::fence_proxy_async_smem();
+  int npairs = 0;
+  for (int g = 0; g < p.G; ++g) npairs += (pair0 + g < p.pairs) ? 1 : 0;
+  ptx::mbar_expect_tx(bar, (uint32_t)npairs * NOPS * p.nbox * p.rows_box * kRowBytes);
+  for (int g = 0; g < p.G; ++g) {
+    const int64_t pr = pair0 + g;
+    if (pr >= p.pairs) break;
+    const int b = (int)(pr / p.sh.H), h = (int)(pr % p.sh.H);
+#pragma unroll
+    for (int t = 0; t < NOPS; ++t)
+      for (int x = 0; x < p.nbox; ++x)
+        tma_load_4d(smem_u32(tiles + g * pair_bytes + t * tile_bytes + (size_t)x * p.rows_box * kRowBytes), tm[t], bar, 0,
+                    h, x * p.rows_box, b);
+  }
+}
+
+// rows [nbox * rows_box, alloc_rows) of every tile are not written by TMA: make them finite (zero)
+__device__ __forceinline__ void zero_tail_rows(uint8_t* tiles, int ntiles_total, size_t tile_bytes, const SeqParams& p) {
+  const int r0 = p.nbox * p.rows_box;
+  const int n16 = (p.alloc_rows - r0) * (kRowBytes / 16);
+  for (int t = 0; t < ntiles_total; ++t)
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      *reinterpret_cast<uint4*>(tiles + t * tile_bytes + (size_t)r0 * kRowBytes + i * 16) = make_uint4(0, 0, 0, 0);
+}
+
+// =================================================================================================================
+// forward
+// =================================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(kMaxThreads) attn_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmq,
+                                                                  const __grid_constant__ CUtensorMap tmk,
+                                                                  const __grid_constant__ CUtensorMap tmv,
+                                                                  __nv_bfloat16* __restrict__ out,
+                                                                  float* __restrict__ lse, SeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // the 128B swizzle is keyed on address bits
+  const Shape& sh = p.sh;
+  const size_t tile_bytes = (size_t)p.alloc_rows * kRowBytes, pair_bytes = 3 * tile_bytes;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + p.G * pair_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair0 = (int64_t)blockIdx.x * p.G;
+  if (threadIdx.x == 0) {
+    const CUtensorMap* const tm[3] = {&tmq, &tmk, &tmv};
+    issue_loads<3>(tm, smem, pair_bytes, tile_bytes, smem_u32(bar), p, pair0);
+  }
+  zero_tail_rows(smem, 3 * p.G, tile_bytes, p);
+  __syncthreads();
+  ptx::mbar_wait(smem_u32(bar), 0);
+
+  const int g = warp / sh.tiles, qt = warp - g * sh.tiles;
+  const int64_t pr = pair0 + g;
+  if (pr >= p.pairs) return;
+  const int b = (int)(pr / sh.H), h = (int)(pr % sh.H);
+  const uint8_t* sQ = smem + g * pair_bytes;
+  const uint8_t* sK = sQ + tile_bytes;
+  const uint8_t* sV = sK + tile_bytes;
+  const int N = sh.N, i0 = qt * 16;
+  uint8_t* sQt = const_cast<uint8_t*>(sQ) + (size_t)i0 * kRowBytes;  // own query tile, later the output staging tile
+  const KeySlots ks = key_slots(i0, N, sh.W);
+  int krow[NT / 2], vrow[NT / 2];
+#pragma unroll
+  for (int x = 0; x < NT / 2; ++x) {
+    krow[x] = max(ks.key(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);        // unused slots read row 0; their P is 0
+    vrow[x] = max(ks.key(16 * x + (lane & 7) + 8 * ((lane >> 3) & 1)), 0);
+  }
+
+  float s[NT][4];
+  scores_rows<NT>(sQt, sK, krow, lane, s);
+
+  const int r0 = lane >> 2;
+  const RowSlots w0 = row_slots(ks, min(i0 + r0, N - 1), N, sh.W), w1 = row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
+  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int slot = nt * 8 + (lane & 3) * 2 + (e & 1);
+      const float val = fmaf(s[nt][e], sh.scale_log2, (e < 2 ? w0 : w1).bias(slot));  // -inf outside the window
+      s[nt][e] = val;
+      if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+    }
+  mx0 = quad_max(mx0);
+  mx1 = quad_max(mx1);
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pe = exp2f(s[nt][e] - (e < 2 ? mx0 : mx1));
+      s[nt][e] = pe;
+      if (e < 2) sum0 += pe; else sum1 += pe;
+    }
+  sum0 = quad_sum(sum0);
+  sum1 = quad_sum(sum1);
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; ++nd)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nd][e] = 0.f;
+  pv_rows<NT>(s, sV, vrow, lane, o);
+
+  __syncwarp();  // the query rows of a tile are read by its own warp only: reuse them as staging
+  stage_acc<HD>(sQt, o, 1.f / sum0, 1.f / sum1, lane);
+  __syncwarp();
+  store_rows<HD>(sQt, lane, [&](int r) {
+    return (i0 + r < N) ? out + (((int64_t)b * N + i0 + r) * sh.H + h) * HD : nullptr;
+  });
+  if ((lane & 3) == 0) {
+    float* l = lse + ((int64_t)b * sh.H + h) * N;
+    if (i0 + r0 < N) l[i0 + r0] = (mx0 + log2f(sum0)) * kLn2;
+    if (i0 + r0 + 8 < N) l[i0 + r0 + 8] = (mx1 + log2f(sum1)) * kLn2;
+  }
+}
+
+// =================================================================================================================
+// backward: phase A (query tiles: delta, dQ), barrier, phase B (key tiles: dK, dV)
+// =================================================================================================================
+template <int NT, int NTK>
+__global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
+    const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+    const __nv_bfloat16* __restrict__ o, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, SeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // the 128B swizzle is keyed on address bits
+  const Shape& sh = p.sh;
+  const size_t tile_bytes = (size_t)p.alloc_rows * kRowBytes, pair_bytes = 4 * tile_bytes;
+  float* sLall = reinterpret_cast<float*>(smem + p.G * pair_bytes);  // [G][alloc_rows] log2-domain LSE (+inf past N)
+  float* sDall = sLall + p.G * p.alloc_rows;                          // [G][alloc_rows] delta
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sDall + p.G * p.alloc_rows);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair0 = (int64_t)blockIdx.x * p.G;
+  if (threadIdx.x == 0) {
+    const CUtensorMap* const tm[4] = {&tmq, &tmk, &tmv, &tmdo};
+    issue_loads<4>(tm, smem, pair_bytes, tile_bytes, smem_u32(bar), p, pair0);
+  }
+  zero_tail_rows(smem, 4 * p.G, tile_bytes, p);
+  __syncthreads();
+  ptx::mbar_wait(smem_u32(bar), 0);
+
+  const int g = warp / sh.tiles, tt = warp - g * sh.tiles;
+  const int64_t pr = pair0 + g;
+  const bool live = pr < p.pairs;
+  const int b = live ? (int)(pr / sh.H) : 0, h = live ? (int)(pr % sh.H) : 0;
+  uint8_t* sQ = smem + g * pair_bytes;
+  uint8_t* sK = sQ + tile_bytes;
+  uint8_t* sV = sK + tile_bytes;
+  uint8_t* sdO = sV + tile_bytes;
+  float* sL = sLall + g * p.alloc_rows;
+  float* sD = sDall + g * p.alloc_rows;
+  const int N = sh.N, t0 = tt * 16;
+  const int64_t base = (int64_t)b * sh.sb + (int64_t)h * sh.sh;
+  const int r0 = lane >> 2;
+
+  // ---------------------------------------------------------------- phase A: queries t0 .. t0+15
+  if (live) {
+    const int i0 = t0;
+    const uint8_t* sQt = sQ + (size_t)i0 * kRowBytes;
+    const uint8_t* sdOt = sdO + (size_t)i0 * kRowBytes;
+    // delta_i = dO_i . O_i: O straight from global (16-byte coalesced), dO from the resident tile
+    {
+      const float* l = lse + ((int64_t)b * sh.H + h) * N;
+      if (lane < 16) sL[i0 + lane] = (i0 + lane < N) ? l[i0 + lane] * kLog2e : CUDART_INF_F;  // +inf -> P = 0
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = (lane >> 3) + 4 * j, c = lane & 7;
+        float part = 0.f;
+        if (i0 + r < N) {
+          const uint4 ov = *reinterpret_cast<const uint4*>(o + (((int64_t)b * N + i0 + r) * sh.H + h) * HD + c * 8);
+          const uint4 dv4 = *reinterpret_cast<const uint4*>(sdOt + tile_off<HD>(r, c));
+          part = bf16x2_dot(ov.x, dv4.x) + bf16x2_dot(ov.y, dv4.y) + bf16x2_dot(ov.z, dv4.z) + bf16x2_dot(ov.w, dv4.w);
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (c == 0) sD[i0 + r] = part;
+      }
+      __syncwarp();
+    }
+    const KeySlots ks = key_slots(i0, N, sh.W);
+    int krow[NT / 2], vrow[NT / 2];
+#pragma unroll
+    for (int x = 0; x < NT / 2; ++x) {
+      krow[x] = max(ks.key(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);
+      vrow[x] = max(ks.key(16 * x + (lane & 7) + 8 * ((lane >> 3) & 1)), 0);
+    }
+    float s[NT][4], dp[NT][4];
+    scores_rows<NT>(sQt, sK, krow, lane, s);
+    scores_rows<NT>(sdOt, sV, krow, lane, dp);
+    const bool ok0 = i0 + r0 < N, ok1 = i0 + r0 + 8 < N;
+    const RowSlots w0 = row_slots(ks, min(i0 + r0, N - 1), N, sh.W), w1 = row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
+    const float L0 = sL[i0 + r0], L1 = sL[i0 + r0 + 8], d0 = sD[i0 + r0], d1 = sD[i0 + r0 + 8];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int slot = nt * 8 + (lane & 3) * 2 + (e & 1);
+        const float pe = exp2f(fmaf(s[nt][e], sh.scale_log2, (e < 2 ? w0 : w1).bias(slot)) - (e < 2 ? L0 : L1));
+        s[nt][e] = pe * (dp[nt][e] - (e < 2 ? d0 : d1));
+      }
+    float acc[HD / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < HD / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+    pv_rows<NT>(s, sK, vrow, lane, acc);  // dQ = scale . dS . K   (vrow: the transposed-load row map)
+    // dQ leaves from the accumulator fragments (the Q rows are still operands of the neighbours' phase B): a quad
+    // writes 16 contiguous bytes, two n-steps complete a 32-byte sector in L2
+    __nv_bfloat16* dq0 = dq + base + (int64_t)(i0 + r0) * sh.sn;
+    store_frag<HD>(acc, sh.scale, dq0, dq0 + 8 * sh.sn, ok0, ok1, sh.colsum ? sh.colsum + h * HD : nullptr, lane);
+  }
+  __syncthreads();  // every delta / LSE is in shared memory; nobody reads K / V band rows any more
+  if (!live) return;
+
+  // ---------------------------------------------------------------- phase B: keys t0 .. t0+15
+  {
+    const int j0 = t0;
+    uint8_t* sKt = sK + (size_t)j0 * kRowBytes;  // own key rows: A operand, later the dK staging tile
+    uint8_t* sVt = sV + (size_t)j0 * kRowBytes;  // own value rows: A operand, later the dV staging tile
+    const QuerySlots qs = query_slots(j0, N, sh.W);
+    int qrowB[NTK / 2], qrowT[NTK / 2];
+#pragma unroll
+    for (int x = 0; x < NTK / 2; ++x) {
+      qrowB[x] = max(qs.query(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);
+      qrowT[x] = max(qs.query(16 * x + (lane & 7) + 8 * ((lane >> 3) & 1)), 0);
+    }
+    float s[NTK][4], dp[NTK][4];
+    scores_rows<NTK>(sKt, sQ, qrowB, lane, s);     // S^T[key][query]
+    scores_rows<NTK>(sVt, sdO, qrowB, lane, dp);   // dP^T[key][query]
+    const int ja = j0 + r0, jb = j0 + r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < NTK; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int slot = nt * 8 + (lane & 3) * 2 + c;
+        const int i = qs.query(slot);
+        const WindowRow w = window_row(max(i, 0), N, sh.W);
+        const float L = i >= 0 ? sL[i] : CUDART_INF_F, dl = i >= 0 ? sD[i] : 0.f;  // unused slots: P = 0
+        const float lb_in = kLog2Int[1 + w.pad], lb_out = kLog2Int[w.pad];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int e = half * 2 + c;
+          const int j = half ? jb : ja;
+          const bool in_band = (unsigned)(j - w.s) < (unsigned)(w.e - w.s);
+          const bool edge = j == w.tgt;
+          const float bias = in_band ? (edge ? lb_in : 0.f) : (edge ? lb_out : -CUDART_INF_F);
+          const float pe = exp2f(fmaf(s[nt][e], sh.scale_log2, bias) - L);
+          s[nt][e] = pe;
+          dp[nt][e] = pe * (dp[nt][e] - dl);
+        }
+      }
+    __syncwarp();  // own K / V rows are dead as operands from here on: reuse them as staging (cheaper than fragment
+                   // stores + shuffled column sums: measured 238 vs 258 us)
+    {
+      float acc[HD / 8][4];
+#pragma unroll
+      for (int nd = 0; nd < HD / 8; ++nd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+      pv_rows<NTK>(s, sdO, qrowT, lane, acc);  // dV = P^T . dO
+      stage_acc<HD>(sVt, acc, 1.f, 1.f, lane);
+    }
+    {
+      float acc[HD / 8][4];
+#pragma unroll
+      for (int nd = 0; nd < HD / 8; ++nd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+      pv_rows<NTK>(dp, sQ, qrowT, lane, acc);  // dK = scale . dS^T . Q
+      stage_acc<HD>(sKt, acc, sh.scale, sh.scale, lane);
+    }
+    __syncwarp();
+    store_rows<HD>(sVt, lane, [&](int r) { return (j0 + r < N) ? dv + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
+    store_rows<HD>(sKt, lane, [&](int r) { return (j0 + r < N) ? dk + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
+    if (sh.colsum) {
+      tile_colsum<HD>(sKt, lane, sh.colsum + (sh.H + h) * HD);
+      tile_colsum<HD>(sVt, lane, sh.colsum + (2 * sh.H + h) * HD);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// [B][N][H][64] bf16 view with element strides (sb, sn, sh); box = 64 x 1 x rows_box x 1
+int make_map(CUtensorMap* tm, const void* ptr, int B, int H, int N, int64_t sb, int64_t sn, int64_t shh, int rows_box) {
+  cuuint64_t gdim[4] = {(cuuint64_t)HD, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)shh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)HD, 1, (cuuint32_t)rows_box, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attn_seq: cuTensorMapEncodeTiled failed with CUresult %d (B=%d H=%d N=%d sb=%lld sn=%lld sh=%lld)", (int)r,
+              B, H, N, (long long)sb, (long long)sn, (long long)shh);
+    return FAVIT_ERR_CUDA;
+  }
+  return FAVIT_OK;
+}
+
+SeqParams make_params(int B, int H, int N, int window, float scale, int64_t sb, int64_t sn, int64_t shh, float* colsum,
+                      int nops) {
+  SeqParams p;
+  const int tiles = ceil_div(N, 16);
+  p.sh = Shape{B, H, N, window, sb, sn, shh, scale * kLog2e, scale, tiles, colsum};
+  p.nbox = ceil_div(N, 256);
+  p.rows_box = ((ceil_div(N, p.nbox) + 7) / 8) * 8;
+  p.alloc_rows = std::max(tiles * 16, p.nbox * p.rows_box);
+  p.pairs = (int64_t)B * H;
+  const size_t per_pair = (size_t)nops * p.alloc_rows * kRowBytes + (nops == 4 ? 2 * p.alloc_rows * 4 : 0);
+  int G = std::max(1, 4 / tiles);  // at least four warps per CTA; short sequences still get many small CTAs per SM
+  G = std::min(G, std::max(1, (int)((100 * 1024) / per_pair)));
+  G = std::min(G, 8);
+  p.G = (int)std::min<int64_t>(G, p.pairs);
+  return p;
+}
+
+}  // namespace
+
+bool attn_seq_applicable(int hd, int window, int N, favit_dtype dtype, const uint8_t* mask, const void* q, const void* k,
+                         const void* v, int64_t sb, int64_t sn, int64_t shh) {
+  auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+  return dtype == FAVIT_BF16 && mask == nullptr && hd == HD && window <= 15 && N >= 1 && N <= 400 && al(q) && al(k) &&
+         al(v) && sb % 8 == 0 && sn % 8 == 0 && shh % 8 == 0 && encode_fn() != nullptr;
+}
+
+int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
+                 float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
+  const SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, nullptr, 3);
+  CUtensorMap tq, tk, tv;
+  if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  if (int rc = make_map(&tv, v, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  const size_t smem = (size_t)p.G * 3 * p.alloc_rows * kRowBytes + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)ceil_div64(p.pairs, p.G);
+  attn_seq_fwd_kernel<4><<<grid, p.G * p.sh.tiles * 32, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)out, lse, p);
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
+                 void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
+                 int64_t shh, cudaStream_t st) {
+  const SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, colsum, 4);
+  CUtensorMap tq, tk, tv, td;
+  if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  if (int rc = make_map(&tv, v, B, H, N, sb, sn, shh, p.rows_box)) return rc;
+  if (int rc = make_map(&td, dout, B, H, N, (int64_t)N * H * HD, (int64_t)H * HD, HD, p.rows_box)) return rc;
+  const size_t smem = (size_t)p.G * (4 * p.alloc_rows * kRowBytes + 2 * p.alloc_rows * 4) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)ceil_div64(p.pairs, p.G);
+  const unsigned threads = p.G * p.sh.tiles * 32;
+  const bool wide = (17 + 4 * (window >> 1)) > 32;  // query slots a key tile may need
+  if (wide)
+    attn_seq_bwd_kernel<4, 6><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse,
+                                                          (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  else
+    attn_seq_bwd_kernel<4, 4><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse,
+                                                          (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+}  // namespace favit

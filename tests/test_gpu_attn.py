@@ -30,6 +30,14 @@ CASES = [
     (1, 1, 129, 64, 7, False),    # a one-row second chunk
     (1, 2, 3, 64, 4, False),      # even window allowed when N <= W
     (1, 2, 4, 128, 4, False),
+    # whole-sequence TMA kernels (head_dim 64, N <= 400): box / tile / CTA-packing edge cases
+    (3, 5, 17, 64, 7, False),     # C2 tokens; 15 sequences, two per CTA -> the last CTA is half empty
+    (1, 1, 16, 64, 7, False),     # exactly one tile, no padding rows
+    (1, 2, 33, 64, 15, False),    # a one-row third tile under a wide window
+    (2, 2, 256, 64, 7, False),    # the largest single TMA box
+    (1, 2, 300, 64, 7, False),    # two boxes per operand, 19 warps
+    (1, 1, 400, 64, 15, False),   # the largest supported sequence, 48 query slots per key tile
+    (1, 2, 401, 64, 7, False),    # one past it: per-warp staging kernels
 ]
 
 

@@ -75,7 +75,11 @@ def main():
     ap.add_argument("--ps", type=int, default=16, help="sppp: patch size")
     ap.add_argument("--K", type=int, default=16, help="sppp: superpixels per image")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--graph", action="store_true", help="time every kernel through a CUDA graph of `iters` launches")
     a = ap.parse_args()
+    if a.graph:
+        global timeit
+        timeit = timeit_graph
     B, N, D, H = a.B, a.N, a.D, a.H
     M = B * N
     hid = 4 * D
