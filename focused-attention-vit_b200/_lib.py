@@ -33,6 +33,8 @@ _SIGS = {
     "favit_gemm_bf16_raw": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp], _i),
     "favit_latent_fold_fwd": ([_vp] * 10 + [_i, _i, _i, _vp], _i),
     "favit_latent_fold_bwd": ([_vp] * 11 + [_i, _i, _vp], _i),
+    "favit_latent_fold_fwd_batched": ([_i, C.POINTER(_vp), _i, _i, _i, _vp], _i),
+    "favit_latent_fold_bwd_batched": ([_i, C.POINTER(_vp), _i, _i, _vp], _i),
     "favit_layernorm_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp], _i),
     "favit_layernorm_bwd": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "favit_sppp_assign": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),

@@ -57,8 +57,8 @@ __device__ __forceinline__ void load_lat(float* sL, const float* __restrict__ la
 // The first column chunk of every head also folds that head's bias: bias_out[h,a] = sum_b bias_in[h,b] M(b,a)
 // (bias_in / bias_out may alias).
 template <typename TOut, bool TRANS>
-__global__ void __launch_bounds__(256) fold_q_kernel(const float* in, TOut* out, const float* __restrict__ lat_w,
-                                                     const float* bias_in, float* bias_out, int H, int hd, int D) {
+__device__ __forceinline__ void fold_q_body(const float* in, TOut* out, const float* __restrict__ lat_w,
+                                            const float* bias_in, float* bias_out, int H, int hd, int D) {
   extern __shared__ float sm[];
   __shared__ float s_vec[64];
   float* sL = sm;             // [hd][hd]
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) fold_q_kernel(const float* in, TOut* out,
 // out[o,h,a] = sum_b in[o,h,b] M(b,a) (+ rowscale[o] * colvec[a]) for 64 rows o and one head h.
 // With bias_out != nullptr (forward) it also adds this head's share of sum_b in[o,h,b] bias_vec[b] to bias_out[o].
 template <typename TOut, bool TRANS>
-__global__ void __launch_bounds__(256) fold_p_kernel(const float* in, TOut* out, const float* __restrict__ lat_w,
-                                                     const float* __restrict__ rowscale,
-                                                     const float* __restrict__ colvec, float* __restrict__ bias_out,
-                                                     const float* __restrict__ bias_vec, int H, int hd, int D) {
+__device__ __forceinline__ void fold_p_body(const float* in, TOut* out, const float* __restrict__ lat_w,
+                                            const float* __restrict__ rowscale, const float* __restrict__ colvec,
+                                            float* __restrict__ bias_out, const float* __restrict__ bias_vec, int H,
+                                            int hd, int D) {
   extern __shared__ float sm[];
   float* sL = sm;             // [hd][hd]
   float* sT = sm + hd * hd;   // [kTile][hd]
@@ -179,14 +179,9 @@ __global__ void __launch_bounds__(256) fold_p_kernel(const float* in, TOut* out,
 
 // forward odds and ends: K/V weight rows cast, folded q bias, K/V bias copy, folded proj bias.
 template <typename TOut>
-__global__ void __launch_bounds__(256) fold_misc_fwd_kernel(const float* __restrict__ qkv_w,
-                                                            const float* __restrict__ qkv_b,
-                                                            const float* __restrict__ proj_w,
-                                                            const float* __restrict__ proj_b,
-                                                            const float* __restrict__ lat_w,
-                                                            const float* __restrict__ lat_b, TOut* __restrict__ wqkv_c,
-                                                            float* __restrict__ bqkv, float* __restrict__ bproj, int H,
-                                                            int hd, int D) {
+__device__ __forceinline__ void fold_misc_fwd_body(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
+                                                   const float* __restrict__ proj_b, TOut* __restrict__ wqkv_c,
+                                                   float* __restrict__ bqkv, float* __restrict__ bproj, int D) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nkv = (int64_t)2 * D * D;
@@ -202,17 +197,15 @@ __global__ void __launch_bounds__(256) fold_misc_fwd_kernel(const float* __restr
 // dWl partial sums.  blockIdx.z == 0: sum over kChunks 64-column chunks of head h of Wq[h,b,c] dWq'[h,a,c] (+ the
 // bias term once per head); blockIdx.z == 1: sum over 64-row chunks of Wp[o,h,b] dWp'[o,h,a], and dbl.
 constexpr int kChunks = 4;
-__global__ void __launch_bounds__(256) fold_dlat_kernel(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
-                                                        const float* __restrict__ proj_w,
-                                                        const float* __restrict__ dwq, const float* __restrict__ dbq,
-                                                        const float* __restrict__ dwp, const float* __restrict__ dbp,
-                                                        float* __restrict__ dlat_w, float* __restrict__ dlat_b, int H,
-                                                        int hd, int D) {
+__device__ __forceinline__ void fold_dlat_body(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
+                                               const float* __restrict__ proj_w, const float* __restrict__ dwq,
+                                               const float* __restrict__ dbq, const float* __restrict__ dwp,
+                                               const float* __restrict__ dbp, float* __restrict__ dlat_w,
+                                               float* __restrict__ dlat_b, int H, int hd, int D, bool proj) {
   extern __shared__ float sm[];
   float* sA = sm;                // q: [kTile c][hd b]   proj: [kTile o][hd b]   (weight tile)
   float* sB = sm + hd * kTile;   // q: [kTile c][hd a]   proj: [kTile o][hd a]   (gradient tile)
   const int h = blockIdx.y;
-  const bool proj = blockIdx.z == 1;
   const int ag = hd / 4;
   const int b4 = (threadIdx.x / ag) * 4, a4 = (threadIdx.x % ag) * 4;   // this thread's 4 x 4 block of dWl
   const bool live = b4 < hd;
@@ -306,6 +299,52 @@ __global__ void __launch_bounds__(256) fold_dbq_kernel(float* dbqkv, const float
   }
 }
 
+
+// ---- batched over layers ----------------------------------------------------------------------------------------
+// The fold is O(D^2 hd) weight-only work; a launch per layer costs more in launch latency than in arithmetic, so every
+// kernel takes the pointers of up to kMaxLayers layers by value (blockIdx.z selects the layer) and one launch serves
+// the whole model.  Pointer order per layer: see favit_latent_fold_fwd_batched / _bwd_batched in include/favit.h.
+constexpr int kMaxLayers = 16;
+constexpr int kFwdPtrs = 10, kBwdPtrs = 11;
+struct FwdTable { const void* p[kMaxLayers][kFwdPtrs]; };
+struct BwdTable { const void* p[kMaxLayers][kBwdPtrs]; };
+#define FP(k) reinterpret_cast<const float*>(t.p[blockIdx.z][k])
+#define FM(k) const_cast<float*>(reinterpret_cast<const float*>(t.p[blockIdx.z][k]))
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) fold_misc_fwd_kernel(const __grid_constant__ FwdTable t, int D) {
+  fold_misc_fwd_body<TOut>(FP(0), FP(1), FP(3), reinterpret_cast<TOut*>(const_cast<void*>(t.p[blockIdx.z][6])), FM(7),
+                           FM(9), D);
+}
+template <typename TOut>
+__global__ void __launch_bounds__(256) fold_q_fwd_kernel(const __grid_constant__ FwdTable t, int H, int hd, int D) {
+  fold_q_body<TOut, false>(FP(0), reinterpret_cast<TOut*>(const_cast<void*>(t.p[blockIdx.z][6])), FP(4), FP(1), FM(7), H,
+                           hd, D);
+}
+template <typename TOut>
+__global__ void __launch_bounds__(256) fold_p_fwd_kernel(const __grid_constant__ FwdTable t, int H, int hd, int D) {
+  fold_p_body<TOut, false>(FP(2), reinterpret_cast<TOut*>(const_cast<void*>(t.p[blockIdx.z][8])), FP(4), nullptr, nullptr,
+                           FM(9), FP(5), H, hd, D);
+}
+#undef FP
+#undef FM
+#define BP(k) reinterpret_cast<const float*>(t.p[layer][k])
+#define BM(k) const_cast<float*>(reinterpret_cast<const float*>(t.p[layer][k]))
+__global__ void __launch_bounds__(256) fold_dlat_kernel(const __grid_constant__ BwdTable t, int H, int hd, int D) {
+  const int layer = blockIdx.z >> 1;
+  fold_dlat_body(BP(0), BP(1), BP(2), BP(5), BP(6), BP(7), BP(8), BM(9), BM(10), H, hd, D, (blockIdx.z & 1) != 0);
+}
+__global__ void __launch_bounds__(256) fold_q_bwd_kernel(const __grid_constant__ BwdTable t, int H, int hd, int D) {
+  const int layer = blockIdx.z;
+  fold_q_body<float, true>(BP(5), BM(5), BP(3), BP(6), BM(6), H, hd, D);
+}
+__global__ void __launch_bounds__(256) fold_p_bwd_kernel(const __grid_constant__ BwdTable t, int H, int hd, int D) {
+  const int layer = blockIdx.z;
+  fold_p_body<float, true>(BP(7), BM(7), BP(3), BP(8), BP(4), nullptr, nullptr, H, hd, D);
+}
+#undef BP
+#undef BM
+
 int check(int H, int hd, const char* who) {
   FAVIT_CHECK_ARG(H > 0 && hd > 0, "%s: H, hd must be positive", who);
   if (hd > 64 || hd % 4 != 0) {
@@ -320,64 +359,92 @@ int check(int H, int hd, const char* who) {
 
 using namespace favit;
 
-extern "C" int favit_latent_fold_fwd(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
-                                     const float* lat_w, const float* lat_b, void* wqkv_c, float* bqkv, void* wproj_c,
-                                     float* bproj, int H, int hd, favit_dtype out_dtype, favit_stream stream) {
-  FAVIT_CHECK_ARG(qkv_w && qkv_b && proj_w && proj_b && lat_w && lat_b && wqkv_c && bqkv && wproj_c && bproj,
-                  "latent_fold_fwd: null pointer");
+extern "C" int favit_latent_fold_fwd_batched(int L, const void* const* ptrs, int H, int hd, favit_dtype out_dtype,
+                                             favit_stream stream) {
+  FAVIT_CHECK_ARG(L > 0 && ptrs, "latent_fold_fwd_batched: L must be > 0 and ptrs non-null");
   if (int rc = check(H, hd, "latent_fold_fwd")) return rc;
+  FAVIT_CHECK_ARG(out_dtype == FAVIT_BF16 || out_dtype == FAVIT_F32, "latent_fold_fwd: bad dtype");
+  for (int i = 0; i < L * kFwdPtrs; ++i) FAVIT_CHECK_ARG(ptrs[i], "latent_fold_fwd: null pointer (entry %d)", i);
   cudaStream_t st = (cudaStream_t)stream;
   const int D = H * hd;
   const size_t smem = (size_t)(hd * hd + hd * kTile) * sizeof(float);
-  const dim3 gq(ceil_div(D, kTile), H), gp(ceil_div(D, kTile), H);
-  if (out_dtype == FAVIT_BF16) {
-    fold_misc_fwd_kernel<__nv_bfloat16><<<2 * num_sms(), 256, 0, st>>>(qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b,
-                                                                       (__nv_bfloat16*)wqkv_c, bqkv, bproj, H, hd, D);
-    FAVIT_CHECK_LAUNCH();
-    fold_q_kernel<__nv_bfloat16, false><<<gq, 256, smem, st>>>(qkv_w, (__nv_bfloat16*)wqkv_c, lat_w, qkv_b, bqkv, H, hd,
-                                                               D);
-    FAVIT_CHECK_LAUNCH();
-    fold_p_kernel<__nv_bfloat16, false><<<gp, 256, smem, st>>>(proj_w, (__nv_bfloat16*)wproj_c, lat_w, nullptr, nullptr,
-                                                               bproj, lat_b, H, hd, D);
-    FAVIT_CHECK_LAUNCH();
-  } else if (out_dtype == FAVIT_F32) {
-    fold_misc_fwd_kernel<float><<<2 * num_sms(), 256, 0, st>>>(qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b,
-                                                               (float*)wqkv_c, bqkv, bproj, H, hd, D);
-    FAVIT_CHECK_LAUNCH();
-    fold_q_kernel<float, false><<<gq, 256, smem, st>>>(qkv_w, (float*)wqkv_c, lat_w, qkv_b, bqkv, H, hd, D);
-    FAVIT_CHECK_LAUNCH();
-    fold_p_kernel<float, false><<<gp, 256, smem, st>>>(proj_w, (float*)wproj_c, lat_w, nullptr, nullptr, bproj, lat_b, H,
-                                                       hd, D);
-    FAVIT_CHECK_LAUNCH();
-  } else {
-    set_error("latent_fold_fwd: bad dtype");
-    return FAVIT_ERR_ARG;
+  for (int l0 = 0; l0 < L; l0 += kMaxLayers) {
+    const int n = L - l0 < kMaxLayers ? L - l0 : kMaxLayers;
+    FwdTable t;
+    for (int l = 0; l < n; ++l)
+      for (int k = 0; k < kFwdPtrs; ++k) t.p[l][k] = ptrs[(size_t)(l0 + l) * kFwdPtrs + k];
+    const dim3 gm(2 * num_sms() / n + 1, 1, n), gq(ceil_div(D, kTile), H, n);
+    if (out_dtype == FAVIT_BF16) {
+      fold_misc_fwd_kernel<__nv_bfloat16><<<gm, 256, 0, st>>>(t, D);
+      FAVIT_CHECK_LAUNCH();
+      fold_q_fwd_kernel<__nv_bfloat16><<<gq, 256, smem, st>>>(t, H, hd, D);
+      FAVIT_CHECK_LAUNCH();
+      fold_p_fwd_kernel<__nv_bfloat16><<<gq, 256, smem, st>>>(t, H, hd, D);
+      FAVIT_CHECK_LAUNCH();
+    } else {
+      fold_misc_fwd_kernel<float><<<gm, 256, 0, st>>>(t, D);
+      FAVIT_CHECK_LAUNCH();
+      fold_q_fwd_kernel<float><<<gq, 256, smem, st>>>(t, H, hd, D);
+      FAVIT_CHECK_LAUNCH();
+      fold_p_fwd_kernel<float><<<gq, 256, smem, st>>>(t, H, hd, D);
+      FAVIT_CHECK_LAUNCH();
+    }
   }
   return FAVIT_OK;
 }
 
-// dwqkv [3D,D], dbqkv [3D], dwproj [D,D] hold the gradients of the FOLDED weights on entry and the gradients of
-// qkv.weight / qkv.bias / proj.weight on exit (transformed in place; the K/V rows and dbproj need no change).
+extern "C" int favit_latent_fold_fwd(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
+                                     const float* lat_w, const float* lat_b, void* wqkv_c, float* bqkv, void* wproj_c,
+                                     float* bproj, int H, int hd, favit_dtype out_dtype, favit_stream stream) {
+  const void* p[kFwdPtrs] = {qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, wqkv_c, bqkv, wproj_c, bproj};
+  return favit_latent_fold_fwd_batched(1, p, H, hd, out_dtype, stream);
+}
+
+// Per layer: dwqkv [3D,D], dbqkv [3D], dwproj [D,D] hold the gradients of the FOLDED weights on entry and the gradients
+// of qkv.weight / qkv.bias / proj.weight on exit (transformed in place; the K/V rows and dbproj need no change).
 // dlat_w [hd,hd] and dlat_b [hd] are overwritten.
+extern "C" int favit_latent_fold_bwd_batched(int L, const void* const* ptrs, int H, int hd, favit_stream stream) {
+  FAVIT_CHECK_ARG(L > 0 && ptrs, "latent_fold_bwd_batched: L must be > 0 and ptrs non-null");
+  if (int rc = check(H, hd, "latent_fold_bwd")) return rc;
+  for (int i = 0; i < L * kBwdPtrs; ++i) FAVIT_CHECK_ARG(ptrs[i], "latent_fold_bwd: null pointer (entry %d)", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = H * hd;
+  const size_t smem = (size_t)(hd * hd + hd * kTile) * sizeof(float);
+  for (int l = 0; l < L; ++l) {
+    float* dlw = const_cast<float*>(reinterpret_cast<const float*>(ptrs[(size_t)l * kBwdPtrs + 9]));
+    float* dlb = const_cast<float*>(reinterpret_cast<const float*>(ptrs[(size_t)l * kBwdPtrs + 10]));
+    if (dlb == dlw + hd * hd) {  // the host side keeps [dlat_w | dlat_b] of a layer (and of all layers) contiguous
+      int run = 1;
+      while (l + run < L && ptrs[(size_t)(l + run) * kBwdPtrs + 9] == (const void*)(dlw + (size_t)run * (hd * hd + hd)) &&
+             ptrs[(size_t)(l + run) * kBwdPtrs + 10] == (const void*)(dlw + (size_t)run * (hd * hd + hd) + hd * hd))
+        ++run;
+      FAVIT_CHECK_CUDA(cudaMemsetAsync(dlw, 0, (size_t)run * (hd * hd + hd) * sizeof(float), st));
+      l += run - 1;
+    } else {
+      FAVIT_CHECK_CUDA(cudaMemsetAsync(dlw, 0, (size_t)hd * hd * sizeof(float), st));
+      FAVIT_CHECK_CUDA(cudaMemsetAsync(dlb, 0, (size_t)hd * sizeof(float), st));
+    }
+  }
+  for (int l0 = 0; l0 < L; l0 += kMaxLayers) {
+    const int n = L - l0 < kMaxLayers ? L - l0 : kMaxLayers;
+    BwdTable t;
+    for (int l = 0; l < n; ++l)
+      for (int k = 0; k < kBwdPtrs; ++k) t.p[l][k] = ptrs[(size_t)(l0 + l) * kBwdPtrs + k];
+    // latent gradients first: they need the gradients of the folded weights as they came in
+    fold_dlat_kernel<<<dim3(ceil_div(ceil_div(D, kTile), kChunks), H, 2 * n), 256,
+                       (size_t)2 * hd * kTile * sizeof(float), st>>>(t, H, hd, D);
+    FAVIT_CHECK_LAUNCH();
+    fold_q_bwd_kernel<<<dim3(ceil_div(D, kTile), H, n), 256, smem, st>>>(t, H, hd, D);
+    FAVIT_CHECK_LAUNCH();
+    fold_p_bwd_kernel<<<dim3(ceil_div(D, kTile), H, n), 256, smem, st>>>(t, H, hd, D);
+    FAVIT_CHECK_LAUNCH();
+  }
+  return FAVIT_OK;
+}
+
 extern "C" int favit_latent_fold_bwd(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* lat_w,
                                      const float* lat_b, float* dwqkv, float* dbqkv, float* dwproj, const float* dbproj,
                                      float* dlat_w, float* dlat_b, int H, int hd, favit_stream stream) {
-  FAVIT_CHECK_ARG(qkv_w && qkv_b && proj_w && lat_w && lat_b && dwqkv && dbqkv && dwproj && dbproj && dlat_w && dlat_b,
-                  "latent_fold_bwd: null pointer");
-  if (int rc = check(H, hd, "latent_fold_bwd")) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int D = H * hd;
-  FAVIT_CHECK_CUDA(cudaMemsetAsync(dlat_w, 0, (size_t)hd * hd * sizeof(float), st));
-  FAVIT_CHECK_CUDA(cudaMemsetAsync(dlat_b, 0, (size_t)hd * sizeof(float), st));
-  // latent gradients first: they need the gradients of the folded weights as they came in
-  fold_dlat_kernel<<<dim3(ceil_div(ceil_div(D, kTile), kChunks), H, 2), 256, (size_t)2 * hd * kTile * sizeof(float), st>>>(
-      qkv_w, qkv_b, proj_w, dwqkv, dbqkv, dwproj, dbproj, dlat_w, dlat_b, H, hd, D);
-  FAVIT_CHECK_LAUNCH();
-  const size_t smem = (size_t)(hd * hd + hd * kTile) * sizeof(float);
-  fold_q_kernel<float, true><<<dim3(ceil_div(D, kTile), H), 256, smem, st>>>(dwqkv, dwqkv, lat_w, dbqkv, dbqkv, H, hd, D);
-  FAVIT_CHECK_LAUNCH();
-  fold_p_kernel<float, true><<<dim3(ceil_div(D, kTile), H), 256, smem, st>>>(dwproj, dwproj, lat_w, dbproj, lat_b, nullptr,
-                                                                             nullptr, H, hd, D);
-  FAVIT_CHECK_LAUNCH();
-  return FAVIT_OK;
+  const void* p[kBwdPtrs] = {qkv_w, qkv_b, proj_w, lat_w, lat_b, dwqkv, dbqkv, dwproj, dbproj, dlat_w, dlat_b};
+  return favit_latent_fold_bwd_batched(1, p, H, hd, stream);
 }

@@ -173,6 +173,101 @@ class FusedBlockFn(torch.autograd.Function):
                 None, None, None, None, None)
 
 
+class BatchedFoldFn(torch.autograd.Function):
+    """latent_proj folded into qkv / proj for ALL blocks of a model in one call (raw.fold_fwd_batched).
+
+    Inputs: 6 fp32 master parameters per layer (qkv.weight, qkv.bias, proj.weight, proj.bias, latent_proj.weight,
+    latent_proj.bias).  Outputs: a one-element fp32 `token` and, per layer, (wqkv', bqkv', wproj', bproj') marked
+    non-differentiable.  The gradients of the folded weights do not travel through autograd (they are fp32 while the
+    folded weights are bf16): every block's backward leaves them in `stash`, and because only the FIRST block consumes
+    `token`, autograd runs this node's backward after the last block backward of the pass, where one batched call maps
+    all of them back to the master parameters."""
+
+    @staticmethod
+    def forward(ctx, H, cd, stash, *params):
+        nl = len(params) // 6
+        f = lambda t: t.detach().float().contiguous()
+        layers = [tuple(f(t) for t in params[6 * i:6 * i + 6]) for i in range(nl)]
+        folded = raw.fold_fwd_batched(layers, H, cd)
+        flat = [t for lay in folded for t in lay]
+        ctx.save_for_backward(*params)
+        ctx.H, ctx.stash = H, stash
+        ctx.mark_non_differentiable(*flat)
+        return (torch.zeros(1, dtype=torch.float32, device=params[0].device), *flat)
+
+    @staticmethod
+    def backward(ctx, gtoken, *unused):
+        params = ctx.saved_tensors
+        nl = len(params) // 6
+        f = lambda t: t.detach().float().contiguous()
+        layers = [tuple(f(params[6 * i + k]) for k in (0, 1, 2, 4, 5)) for i in range(nl)]
+        grads = [ctx.stash.pop(i) for i in range(nl)]
+        dl = raw.fold_bwd_batched(layers, grads, ctx.H)
+        out = []
+        for (dwq, dbq, dwp, dbp), (dlw, dlb) in zip(grads, dl):
+            out += [dwq, dbq, dwp, dbp, dlw, dlb]
+        return (None, None, None, *out)
+
+
+class FusedBlockPrefoldedFn(torch.autograd.Function):
+    """FusedBlockFn with the folded qkv / proj weights supplied by BatchedFoldFn (see there for `token` / `stash`)."""
+
+    @staticmethod
+    def forward(ctx, x, token, ln1_w, ln1_b, ln2_w, ln2_b, w1, b1, w2, b2, wq_c, bq, wp_c, bp, layer, stash, H, window,
+                eps1, eps2, cd):
+        B, N, D = x.shape
+        x2d = x.reshape(B * N, D)
+        if not x2d.is_contiguous():
+            x2d = x2d.contiguous()
+        c = (lambda t: t.detach().to(cd)) if cd != torch.float32 else (lambda t: t.detach().contiguous())
+        f = lambda t: t.detach().float().contiguous()
+        w1_c, w2_c = c(w1), c(w2)
+        outs = block_fwd(x2d.detach(), f(ln1_w), f(ln1_b), wq_c, bq, wp_c, bp, f(ln2_w), f(ln2_b), w1_c, f(b1), w2_c,
+                         f(b2), B, N, H, window, eps1, eps2)
+        ctx.save_for_backward(x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *outs[1:])
+        ctx.dims = (B, N, H, window)
+        ctx.layer, ctx.stash, ctx.has_token = layer, stash, token is not None
+        return outs[0].view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *saved = ctx.saved_tensors
+        B, N, H, window = ctx.dims
+        D = x2d.shape[1]
+        g2d = g.reshape(B * N, D)
+        if g2d.dtype != torch.float32:
+            g2d = g2d.float()
+        f = lambda t: t.detach().float().contiguous()
+        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = block_bwd(
+            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window)
+        ctx.stash[ctx.layer] = (dwq, dbq, dwp, dbp)
+        gtok = torch.zeros(1, dtype=torch.float32, device=dx.device) if ctx.has_token else None
+        return (dx.view(B, N, D), gtok, dln1_w, dln1_b, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None, None,
+                None, None, None, None, None, None)
+
+
+def run_blocks(blocks, x: Tensor, compute_dtype: torch.dtype) -> Tensor:
+    """x through a list of TransformerBlock-like modules (attributes norm1, attn, norm2, mlp.fc1, mlp.fc2), every one of
+    which the caller found `fusable`: the latent fold of all blocks is one launch set per pass instead of one per block."""
+    attn0 = blocks[0].attn
+    H, window = attn0.num_heads, attn0.window_size
+    params = []
+    for blk in blocks:
+        a = blk.attn
+        params += [a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, a.latent_proj.weight, a.latent_proj.bias]
+    stash = {}
+    token, *flat = BatchedFoldFn.apply(H, compute_dtype, stash, *params)
+    if not token.requires_grad:
+        token = None
+    for i, blk in enumerate(blocks):
+        wq_c, bq, wp_c, bp = flat[4 * i:4 * i + 4]
+        fc1, fc2 = blk.mlp.fc1, blk.mlp.fc2
+        x = FusedBlockPrefoldedFn.apply(x, token if i == 0 else None, blk.norm1.weight, blk.norm1.bias, blk.norm2.weight,
+                                        blk.norm2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, wq_c, bq, wp_c, bp, i,
+                                        stash, H, window, blk.norm1.eps, blk.norm2.eps, compute_dtype)
+    return x
+
+
 def fused_block(x, ln1, attn, ln2, fc1, fc2, compute_dtype: torch.dtype):
     """attn: a MultiHeadLatentAttention module (qkv / proj / latent_proj parameters are read directly)."""
     return FusedBlockFn.apply(x, ln1.weight, ln1.bias, attn.qkv.weight, attn.qkv.bias, attn.proj.weight,

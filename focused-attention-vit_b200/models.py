@@ -103,6 +103,24 @@ class TransformerBlock(nn.Module):
         return x
 
 
+def run_blocks(blocks, x: torch.Tensor) -> torch.Tensor:
+    """The block stack of both models.  When every block takes the fused path the latent fold of all of them is
+    batched (fused_block.run_blocks); otherwise blocks run one by one."""
+    blks = list(blocks)
+    cd = compute_dtype(x)
+    a0 = blks[0].attn if blks and getattr(blks[0], "use_mhla", False) else None
+    if a0 is not None and len(blks) > 1 and all(
+            isinstance(b, TransformerBlock) and b.use_mhla and b.attn.num_heads == a0.num_heads and
+            b.attn.window_size == a0.window_size and b.attn.embed_dim == a0.embed_dim and
+            fused_block.fusable(x, b.attn, b.mlp.dropout.p, b.training, None, cd, b.mlp.fc1.out_features)
+            for b in blks):
+        with torch.autocast("cuda", enabled=False):
+            return fused_block.run_blocks(blks, x, cd)
+    for block in blks:
+        x = block(x)
+    return x
+
+
 def _init_weights_recursive(m):
     if isinstance(m, nn.Linear):
         nn.init.normal_(m.weight, std=0.02)
@@ -152,9 +170,7 @@ class VisionTransformerMHLA(nn.Module):
         batch_size = x.shape[0]
         x = self.patch_embed(x)
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), x), dim=1)
-        x = self.pos_drop(x + self.pos_embed)
-        for block in self.blocks:
-            x = block(x)
+        x = run_blocks(self.blocks, self.pos_drop(x + self.pos_embed))
         # LayerNorm is per token and only the class token is used (vit_mhla.py:241-244): normalise that row alone
         return self.norm(x[:, 0])
 
@@ -283,9 +299,7 @@ class SPPPViTMHLA(nn.Module):
         pooled = self.pooling.pool_batch(patch_embeddings, assignment, self.num_superpixels,
                                          validate=self.validate_slots)
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), pooled), dim=1)
-        x = self.pos_embed(x, self._calculate_superpixel_centroids(segmentation_maps))
-        for block in self.blocks:
-            x = block(x)
+        x = run_blocks(self.blocks, self.pos_embed(x, self._calculate_superpixel_centroids(segmentation_maps)))
         # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone
         return self.head(self.norm(x[:, 0]))
 

@@ -136,6 +136,47 @@ def fold_fwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, proj_b: Tensor, lat_w
     return wq, bq, wp, bp
 
 
+def fold_fwd_batched(layers, H: int, cd: torch.dtype):
+    """layers: list of (qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b) fp32 tensors of the L blocks of one model.
+    One call for the whole model; returns L tuples (wqkv' cd, bqkv' fp32, wproj' cd, bproj' fp32), views of four
+    contiguous [L, ...] buffers."""
+    import ctypes as C
+    nl = len(layers)
+    D = layers[0][2].shape[0]
+    hd = D // H
+    dev = layers[0][0].device
+    wq = torch.empty((nl, 3 * D, D), dtype=cd, device=dev)
+    wp = torch.empty((nl, D, D), dtype=cd, device=dev)
+    bq = torch.empty((nl, 3 * D), dtype=torch.float32, device=dev)
+    bp = torch.empty((nl, D), dtype=torch.float32, device=dev)
+    ptrs = []
+    for i, lay in enumerate(layers):
+        ptrs += [t.data_ptr() for t in lay] + [wq[i].data_ptr(), bq[i].data_ptr(), wp[i].data_ptr(), bp[i].data_ptr()]
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    rc = L.call("fold", 0.0, L.lib().favit_latent_fold_fwd_batched, nl, arr, H, hd, _DT[cd], _s())
+    L.check(rc, "favit_latent_fold_fwd_batched")
+    return [(wq[i], bq[i], wp[i], bp[i]) for i in range(nl)]
+
+
+def fold_bwd_batched(layers, grads, H: int):
+    """layers: list of (qkv_w, qkv_b, proj_w, lat_w, lat_b); grads: list of (dwqkv, dbqkv, dwproj, dbproj), the
+    gradients of the folded weights, rewritten IN PLACE into the gradients of qkv.weight / qkv.bias / proj.weight.
+    Returns L tuples (dlat_w, dlat_b)."""
+    import ctypes as C
+    nl = len(layers)
+    D = layers[0][2].shape[0]
+    hd = D // H
+    dl = torch.empty((nl, hd * hd + hd), dtype=torch.float32, device=layers[0][0].device)
+    ptrs = []
+    for i in range(nl):
+        ptrs += [t.data_ptr() for t in layers[i]] + [t.data_ptr() for t in grads[i]]
+        ptrs += [dl[i].data_ptr(), dl[i, hd * hd:].data_ptr()]
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    rc = L.call("fold", 0.0, L.lib().favit_latent_fold_bwd_batched, nl, arr, H, hd, _s())
+    L.check(rc, "favit_latent_fold_bwd_batched")
+    return [(dl[i, :hd * hd].view(hd, hd), dl[i, hd * hd:]) for i in range(nl)]
+
+
 def fold_bwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, lat_w: Tensor, lat_b: Tensor, dwqkv: Tensor, dbqkv: Tensor,
              dwproj: Tensor, dbproj: Tensor, H: int):
     """In place: dwqkv / dbqkv / dwproj become the gradients of qkv.weight / qkv.bias / proj.weight.

@@ -139,6 +139,17 @@ int favit_latent_fold_bwd(const float* qkv_w, const float* qkv_b, const float* p
                           const float* lat_b, float* dwqkv, float* dbqkv, float* dwproj, const float* dbproj,
                           float* dlat_w, float* dlat_b, int H, int hd, favit_stream stream);
 
+/* The same two folds for L layers of one model in one call (the work is weight-only and tiny: a launch per layer
+ * costs more than the arithmetic).  ptrs is a HOST array of L rows of device pointers, in the argument order of the
+ * single-layer functions:
+ *   fwd, 10 per layer: qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, wqkv_c, bqkv, wproj_c, bproj
+ *   bwd, 11 per layer: qkv_w, qkv_b, proj_w, lat_w, lat_b, dwqkv, dbqkv, dwproj, dbproj, dlat_w, dlat_b
+ * All layers share H, hd and (fwd) out_dtype. */
+int favit_latent_fold_fwd_batched(int L, const void* const* ptrs, int H, int hd, favit_dtype out_dtype,
+                                  favit_stream stream);
+
+int favit_latent_fold_bwd_batched(int L, const void* const* ptrs, int H, int hd, favit_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm around the attention / MLP — "next" row: nn.LayerNorm at models/vit_mhla.py:88,107
  * (norm1 / norm2 of the block) and its autograd.  fp32 statistics; D % 4 == 0, D <= 1024.
