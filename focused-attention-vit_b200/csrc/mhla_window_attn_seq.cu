@@ -214,14 +214,71 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_fwd_kernel(const __grid_
 }
 
 // =================================================================================================================
-// backward: phase A (query tiles: delta, dQ), barrier, phase B (key tiles: dK, dV)
+// backward: phase A (query tiles: delta, P, dS, dQ), barrier, P / dS parked as bf16 band blocks, barrier,
+//           phase B (key tiles: dV = P^T.dO, dK = scale.dS^T.Q straight from the parked blocks)
 // =================================================================================================================
-template <int NT, int NTK>
+// Phase A numbers the key slots of query tile i0 in ALIGNED coordinates: slot s <-> key i0 - 8 + s for s in 1..30 (the
+// band i0-h .. i0+15+h fits for h <= 7), slot 0 <-> the duplicated edge key N-1, slot 31 <-> the duplicated edge key 0.
+// A duplicate goes to its edge slot unless the edge key lies inside the query's OWN window (then the band slot carries
+// multiplicity 1 + pad), so every non-edge entry of P / dS sits within h of the diagonal.  The 16 x 32 blocks P and dS
+// of every tile are then 8-aligned in key space: a key tile finds the six 8 x 8 blocks that touch it at fixed chunk
+// positions of its own and its two neighbour query tiles, transposes them with ldmatrix.trans, and never recomputes a
+// score; the first / last key tile add one k-step for what the edge slots hold.
+struct AlSlots {
+  int base, lo, hi, exA, exB, N;
+  __device__ __forceinline__ int key(int s) const {
+    if (s == 0) return exA ? N - 1 : -1;
+    if (s == 31) return exB ? 0 : -1;
+    const int j = base + s;
+    return (j >= lo && j <= hi) ? j : -1;
+  }
+};
+__device__ __forceinline__ AlSlots al_slots(int i0, int N, int W) {
+  const int h = W >> 1;
+  AlSlots k;
+  k.N = N;
+  k.base = i0 - 8;
+  k.lo = max(0, i0 - h);
+  k.hi = min(N - 1, i0 + 15 + h);
+  k.exA = (i0 == 0) ? 1 : 0;  // early queries (i <= h, the only ones that duplicate key N-1) live in the first tile
+  k.exB = 1;
+  return k;
+}
+__device__ __forceinline__ RowSlots al_row_slots(const AlSlots& k, int i, int N, int W) {
+  const WindowRow r = window_row(i, N, W);
+  RowSlots o;
+  o.s_lo = r.s - k.base;
+  o.s_span = r.e - 1 - r.s;
+  if (r.tgt >= r.s && r.tgt < r.e) o.ts = r.tgt - k.base;       // inside the query's own window: band slot
+  else o.ts = (r.s == 0) ? (k.exA ? 0 : -1) : 31;               // else the edge slot of key N-1 / key 0
+  if (r.pad == 0) o.ts = -1;
+  o.lb_in = kLog2Int[1 + r.pad];
+  o.lb_out = kLog2Int[r.pad];
+  return o;
+}
+
+constexpr int kBlkBytes = 16 * 32 * 2;  // one parked 16 x 32 bf16 block (rows of 64 bytes, tile_off<32> swizzle)
+
+// acc[8][4] += A . rows(16 x 64), A given as ready fragments, B rows = sequence rows brow (load_bt lane pattern)
+__device__ __forceinline__ void mma_rows(const uint32_t (&a)[4], const uint8_t* sRows, int brow, int lane,
+                                         float (&acc)[HD / 8][4]) {
+  const uint32_t rbase = smem_u32(sRows);
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; nd += 2) {
+    uint32_t b[4];
+    ldsm_x4_trans(rbase + row_off(brow, nd + (lane >> 4)), b);
+    mma_bf16(acc[nd], a, b[0], b[1]);
+    mma_bf16(acc[nd + 1], a, b[2], b[3]);
+  }
+}
+
+template <int NT>
 __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
     const __nv_bfloat16* __restrict__ o, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
     __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, SeqParams p) {
+  static_assert(NT == 4, "32 aligned key slots per query tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // the 128B swizzle is keyed on address bits
   const Shape& sh = p.sh;
@@ -229,29 +286,33 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
   float* sLall = reinterpret_cast<float*>(smem + p.G * pair_bytes);  // [G][alloc_rows] log2-domain LSE (+inf past N)
   float* sDall = sLall + p.G * p.alloc_rows;                          // [G][alloc_rows] delta
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sDall + p.G * p.alloc_rows);
+  uint8_t* zero16 = reinterpret_cast<uint8_t*>(bar + 2);              // 16 zero bytes: the absent 8 x 8 blocks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pair0 = (int64_t)blockIdx.x * p.G;
   if (threadIdx.x == 0) {
     const CUtensorMap* const tm[4] = {&tmq, &tmk, &tmv, &tmdo};
     issue_loads<4>(tm, smem, pair_bytes, tile_bytes, smem_u32(bar), p, pair0);
   }
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(zero16)[threadIdx.x] = 0u;
   zero_tail_rows(smem, 4 * p.G, tile_bytes, p);
   __syncthreads();
   ptx::mbar_wait(smem_u32(bar), 0);
 
-  const int g = warp / sh.tiles, tt = warp - g * sh.tiles;
+  const int tiles = sh.tiles;
+  const int g = warp / tiles, tt = warp - g * tiles;
   const int64_t pr = pair0 + g;
   const bool live = pr < p.pairs;
   const int b = live ? (int)(pr / sh.H) : 0, h = live ? (int)(pr % sh.H) : 0;
   uint8_t* sQ = smem + g * pair_bytes;
-  uint8_t* sK = sQ + tile_bytes;
-  uint8_t* sV = sK + tile_bytes;
+  uint8_t* sK = sQ + tile_bytes;    // after phase A: the parked P blocks [tiles][16][32], then the dS blocks
+  uint8_t* sV = sK + tile_bytes;    // after phase A: output staging
   uint8_t* sdO = sV + tile_bytes;
   float* sL = sLall + g * p.alloc_rows;
   float* sD = sDall + g * p.alloc_rows;
   const int N = sh.N, t0 = tt * 16;
   const int64_t base = (int64_t)b * sh.sb + (int64_t)h * sh.sh;
   const int r0 = lane >> 2;
+  uint32_t p_pk[NT][2], ds_pk[NT][2];  // this tile's P and dS, bf16 pairs in accumulator-fragment order
 
   // ---------------------------------------------------------------- phase A: queries t0 .. t0+15
   if (live) {
@@ -278,104 +339,145 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
       }
       __syncwarp();
     }
-    const KeySlots ks = key_slots(i0, N, sh.W);
+    const AlSlots ks = al_slots(i0, N, sh.W);
     int krow[NT / 2], vrow[NT / 2];
 #pragma unroll
     for (int x = 0; x < NT / 2; ++x) {
-      krow[x] = max(ks.key(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);
+      krow[x] = max(ks.key(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);        // unused slots read row 0; their P is 0
       vrow[x] = max(ks.key(16 * x + (lane & 7) + 8 * ((lane >> 3) & 1)), 0);
     }
     float s[NT][4], dp[NT][4];
     scores_rows<NT>(sQt, sK, krow, lane, s);
     scores_rows<NT>(sdOt, sV, krow, lane, dp);
     const bool ok0 = i0 + r0 < N, ok1 = i0 + r0 + 8 < N;
-    const RowSlots w0 = row_slots(ks, min(i0 + r0, N - 1), N, sh.W), w1 = row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
+    const RowSlots w0 = al_row_slots(ks, min(i0 + r0, N - 1), N, sh.W);
+    const RowSlots w1 = al_row_slots(ks, min(i0 + r0 + 8, N - 1), N, sh.W);
     const float L0 = sL[i0 + r0], L1 = sL[i0 + r0 + 8], d0 = sD[i0 + r0], d1 = sD[i0 + r0 + 8];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int slot = nt * 8 + (lane & 3) * 2 + (e & 1);
         const float pe = exp2f(fmaf(s[nt][e], sh.scale_log2, (e < 2 ? w0 : w1).bias(slot)) - (e < 2 ? L0 : L1));
         s[nt][e] = pe * (dp[nt][e] - (e < 2 ? d0 : d1));
+        dp[nt][e] = pe;
       }
+      p_pk[nt][0] = pack_bf16x2(dp[nt][0], dp[nt][1]);
+      p_pk[nt][1] = pack_bf16x2(dp[nt][2], dp[nt][3]);
+      ds_pk[nt][0] = pack_bf16x2(s[nt][0], s[nt][1]);
+      ds_pk[nt][1] = pack_bf16x2(s[nt][2], s[nt][3]);
+    }
     float acc[HD / 8][4];
 #pragma unroll
     for (int nd = 0; nd < HD / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-    pv_rows<NT>(s, sK, vrow, lane, acc);  // dQ = scale . dS . K   (vrow: the transposed-load row map)
-    // dQ leaves from the accumulator fragments (the Q rows are still operands of the neighbours' phase B): a quad
-    // writes 16 contiguous bytes, two n-steps complete a 32-byte sector in L2
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {  // dQ = scale . dS . K
+      const uint32_t a[4] = {ds_pk[2 * kk][0], ds_pk[2 * kk][1], ds_pk[2 * kk + 1][0], ds_pk[2 * kk + 1][1]};
+      mma_rows(a, sK, vrow[kk], lane, acc);
+    }
+    // dQ leaves from the accumulator fragments (the Q rows are operands of the neighbours' phase B): a quad writes
+    // 16 contiguous bytes, two n-steps complete a 32-byte sector in L2
     __nv_bfloat16* dq0 = dq + base + (int64_t)(i0 + r0) * sh.sn;
     store_frag<HD>(acc, sh.scale, dq0, dq0 + 8 * sh.sn, ok0, ok1, sh.colsum ? sh.colsum + h * HD : nullptr, lane);
   }
-  __syncthreads();  // every delta / LSE is in shared memory; nobody reads K / V band rows any more
+  __syncthreads();  // nobody reads K / V band rows any more
+  if (live) {       // park P in the K tile's first half, dS in its second half
+    uint8_t* pP = sK + (size_t)tt * kBlkBytes;
+    uint8_t* pS = pP + (size_t)tiles * kBlkBytes;
+    const int sub = (lane & 3) * 4;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      *reinterpret_cast<uint32_t*>(pP + tile_off<32>(r0, nt) + sub) = p_pk[nt][0];
+      *reinterpret_cast<uint32_t*>(pP + tile_off<32>(r0 + 8, nt) + sub) = p_pk[nt][1];
+      *reinterpret_cast<uint32_t*>(pS + tile_off<32>(r0, nt) + sub) = ds_pk[nt][0];
+      *reinterpret_cast<uint32_t*>(pS + tile_off<32>(r0 + 8, nt) + sub) = ds_pk[nt][1];
+    }
+  }
+  __syncthreads();
   if (!live) return;
 
   // ---------------------------------------------------------------- phase B: keys t0 .. t0+15
   {
     const int j0 = t0;
-    uint8_t* sKt = sK + (size_t)j0 * kRowBytes;  // own key rows: A operand, later the dK staging tile
-    uint8_t* sVt = sV + (size_t)j0 * kRowBytes;  // own value rows: A operand, later the dV staging tile
-    const QuerySlots qs = query_slots(j0, N, sh.W);
-    int qrowB[NTK / 2], qrowT[NTK / 2];
-#pragma unroll
-    for (int x = 0; x < NTK / 2; ++x) {
-      qrowB[x] = max(qs.query(16 * x + (lane & 7) + 8 * (lane >> 4)), 0);
-      qrowT[x] = max(qs.query(16 * x + (lane & 7) + 8 * ((lane >> 3) & 1)), 0);
+    const uint8_t* sP = sK;
+    const uint8_t* sS = sK + (size_t)tiles * kBlkBytes;
+    const uint32_t zaddr = smem_u32(zero16);
+    // ldmatrix.x4.trans row addresses of the A fragments P^T / dS^T (offsets relative to sP / sS):
+    //   k-step 0: queries [j0-8, j0+8) = tile t-1 rows 8-15, tile t rows 0-7; k-step 1: [j0+8, j0+24) = tile t rows
+    //   8-15, tile t+1 rows 0-7.  Matrix m of the x4 = lanes 8m..8m+7: (k half, key half) = (m >> 1, m & 1).
+    const int mi = lane >> 3, r8 = lane & 7;
+    int offA[2];
+    {
+      // k-step 0: m0 (t-1, rows 8.., chunk 3)  m1 zero                 m2 (t, rows 0.., chunk 1)  m3 (t, rows 0.., chunk 2)
+      // k-step 1: m0 (t, rows 8.., chunk 1)    m1 (t, rows 8.., chunk 2) m2 zero                  m3 (t+1, rows 0.., chunk 0)
+      const int q0 = (mi == 0) ? tt - 1 : tt, rr0 = (mi == 0) ? 8 + r8 : r8, c0 = (mi == 0) ? 3 : mi - 1;
+      offA[0] = (mi == 1 || q0 < 0) ? -1 : q0 * kBlkBytes + (int)tile_off<32>(rr0, c0);
+      const int q1 = (mi == 3) ? tt + 1 : tt, rr1 = (mi == 3) ? r8 : 8 + r8, c1 = (mi == 3) ? 0 : mi + 1;
+      offA[1] = (mi == 2 || q1 >= tiles) ? -1 : q1 * kBlkBytes + (int)tile_off<32>(rr1, c1);
     }
-    float s[NTK][4], dp[NTK][4];
-    scores_rows<NTK>(sKt, sQ, qrowB, lane, s);     // S^T[key][query]
-    scores_rows<NTK>(sVt, sdO, qrowB, lane, dp);   // dP^T[key][query]
+    int brow[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+      brow[kk] = min(max(j0 - 8 + 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), 0), p.alloc_rows - 1);
     const int ja = j0 + r0, jb = j0 + r0 + 8;
-#pragma unroll
-    for (int nt = 0; nt < NTK; ++nt)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int slot = nt * 8 + (lane & 3) * 2 + c;
-        const int i = qs.query(slot);
-        const WindowRow w = window_row(max(i, 0), N, sh.W);
-        const float L = i >= 0 ? sL[i] : CUDART_INF_F, dl = i >= 0 ? sD[i] : 0.f;  // unused slots: P = 0
-        const float lb_in = kLog2Int[1 + w.pad], lb_out = kLog2Int[w.pad];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int e = half * 2 + c;
-          const int j = half ? jb : ja;
-          const bool in_band = (unsigned)(j - w.s) < (unsigned)(w.e - w.s);
-          const bool edge = j == w.tgt;
-          const float bias = in_band ? (edge ? lb_in : 0.f) : (edge ? lb_out : -CUDART_INF_F);
-          const float pe = exp2f(fmaf(s[nt][e], sh.scale_log2, bias) - L);
-          s[nt][e] = pe;
-          dp[nt][e] = pe * (dp[nt][e] - dl);
-        }
+    const bool okA = ja < N, okB = jb < N;
+    // edge keys: key N-1 (last tile) collects slot 0 of queries 0..15, key 0 (first tile) collects slot 31 of the last
+    // 16 queries (late queries are within h of the end); rows that duplicate nothing parked zeros there
+    const int tlast = (N - 1) >> 4;
+    const bool edgeA = tt == tlast, edgeB = tt == 0;
+    const int qb = max(N - 16, 0);
+    const int k0 = (lane & 3) * 2;
+    auto val = [&](const uint8_t* blocks, int q, int slot) -> uint32_t {  // bf16 bits parked for query q, slot `slot`
+      return *reinterpret_cast<const uint16_t*>(blocks + (size_t)(q >> 4) * kBlkBytes + tile_off<32>(q & 15, slot >> 3) +
+                                                (slot & 7) * 2);
+    };
+    auto edge_frag = [&](const uint8_t* blocks, bool keyA, uint32_t (&a)[4]) {
+      a[0] = a[1] = a[2] = a[3] = 0u;
+      const int R = keyA ? (N - 1) & 15 : 0;       // row of the edge key in this tile
+      const int q = keyA ? k0 : qb + k0, slot = keyA ? 0 : 31;
+      if (r0 == (R & 7)) {  // A[R][k] = value(query q_first + k, slot)
+        const uint32_t lo = val(blocks, q, slot) | (val(blocks, q + 1, slot) << 16);
+        const uint32_t hi = val(blocks, q + 8, slot) | (val(blocks, q + 9, slot) << 16);
+        if (R < 8) { a[0] = lo; a[2] = hi; } else { a[1] = lo; a[3] = hi; }
       }
-    __syncwarp();  // own K / V rows are dead as operands from here on: reuse them as staging (cheaper than fragment
-                   // stores + shuffled column sums: measured 238 vs 258 us)
-    {
+    };
+    const int erowA = (lane & 7) + 8 * ((lane >> 3) & 1), erowB = qb + erowA;  // B rows of the edge steps
+    uint8_t* stage = sV + (size_t)j0 * kRowBytes;  // the V rows of this tile: free since the barrier
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {  // 0: dV = P^T . dO     1: dK = scale . dS^T . Q
+      const uint8_t* blocks = pass == 0 ? sP : sS;
+      const uint8_t* rows = pass == 0 ? sdO : sQ;
+      const uint32_t bbase = smem_u32(blocks);
       float acc[HD / 8][4];
 #pragma unroll
       for (int nd = 0; nd < HD / 8; ++nd)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-      pv_rows<NTK>(s, sdO, qrowT, lane, acc);  // dV = P^T . dO
-      stage_acc<HD>(sVt, acc, 1.f, 1.f, lane);
-    }
-    {
-      float acc[HD / 8][4];
 #pragma unroll
-      for (int nd = 0; nd < HD / 8; ++nd)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-      pv_rows<NTK>(dp, sQ, qrowT, lane, acc);  // dK = scale . dS^T . Q
-      stage_acc<HD>(sKt, acc, sh.scale, sh.scale, lane);
-    }
-    __syncwarp();
-    store_rows<HD>(sVt, lane, [&](int r) { return (j0 + r < N) ? dv + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
-    store_rows<HD>(sKt, lane, [&](int r) { return (j0 + r < N) ? dk + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
-    if (sh.colsum) {
-      tile_colsum<HD>(sKt, lane, sh.colsum + (sh.H + h) * HD);
-      tile_colsum<HD>(sVt, lane, sh.colsum + (2 * sh.H + h) * HD);
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t a[4];
+        ldsm_x4_trans(offA[kk] >= 0 ? bbase + (uint32_t)offA[kk] : zaddr, a);
+        mma_rows(a, rows, brow[kk], lane, acc);
+      }
+      if (edgeA) {  // warp-uniform
+        uint32_t a[4];
+        edge_frag(blocks, true, a);
+        mma_rows(a, rows, erowA, lane, acc);
+      }
+      if (edgeB) {
+        uint32_t a[4];
+        edge_frag(blocks, false, a);
+        mma_rows(a, rows, erowB, lane, acc);
+      }
+      const float m = pass == 0 ? 1.f : sh.scale;
+      __syncwarp();
+      stage_acc<HD>(stage, acc, okA ? m : 0.f, okB ? m : 0.f, lane);  // rows past N must stay exact zeros (column sums)
+      __syncwarp();
+      __nv_bfloat16* dst = pass == 0 ? dv : dk;
+      store_rows<HD>(stage, lane, [&](int r) { return (j0 + r < N) ? dst + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
+      if (sh.colsum) tile_colsum<HD>(stage, lane, sh.colsum + ((pass == 0 ? 2 : 1) * sh.H + h) * HD);
     }
   }
 }
@@ -471,22 +573,16 @@ int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, con
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&tv, v, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&td, dout, B, H, N, (int64_t)N * H * HD, (int64_t)H * HD, HD, p.rows_box)) return rc;
-  const size_t smem = (size_t)p.G * (4 * p.alloc_rows * kRowBytes + 2 * p.alloc_rows * 4) + 16 + 1024;
+  const size_t smem = (size_t)p.G * (4 * p.alloc_rows * kRowBytes + 2 * p.alloc_rows * 4) + 32 + 1024;
   static bool configured = false;
   if (!configured) {
-    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div64(p.pairs, p.G);
   const unsigned threads = p.G * p.sh.tiles * 32;
-  const bool wide = (17 + 4 * (window >> 1)) > 32;  // query slots a key tile may need
-  if (wide)
-    attn_seq_bwd_kernel<4, 6><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse,
-                                                          (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
-  else
-    attn_seq_bwd_kernel<4, 4><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse,
-                                                          (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  attn_seq_bwd_kernel<4><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse, (__nv_bfloat16*)dq,
+                                                      (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }
