@@ -169,6 +169,14 @@ __device__ __forceinline__ void store_frag(const float (&acc)[HD / 8][4], float 
   }
 }
 
+// 8 x 8 b16 transpose across the warp: fragment (row lane/4, cols 2*(lane%4)+{0,1}) -> the same of the transposed matrix
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+constexpr uint32_t kOnesBf16x2 = 0x3f803f80u;  // {1.0, 1.0} in bf16
+
 // column sums of a staged 16-row tile (rows past the end of the sequence hold exact zeros) added to dst[0..HD)
 template <int HD>
 __device__ __forceinline__ void tile_colsum(const uint8_t* tile, int lane, float* dst) {

@@ -272,6 +272,39 @@ __device__ __forceinline__ void mma_rows(const uint32_t (&a)[4], const uint8_t* 
   }
 }
 
+// Column sums on the tensor pipe: ones(16 x 16) . X(16 x 64) leaves the 64 sums in every row of the accumulator; lanes
+// 0-3 (row 0) add them to dst.  X = a staged tile (bf16 rows in shared memory) ...
+__device__ __forceinline__ void colsum_staged(const uint8_t* stage, int lane, float* dst) {
+  const uint32_t ones[4] = {kOnesBf16x2, kOnesBf16x2, kOnesBf16x2, kOnesBf16x2};
+  float acc[HD / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; ++nd)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+  mma_rows(ones, stage, (lane & 7) + 8 * ((lane >> 3) & 1), lane, acc);
+  if (lane < 4) {
+#pragma unroll
+    for (int nd = 0; nd < HD / 8; ++nd) {
+      atomicAdd(dst + nd * 8 + lane * 2, acc[nd][0]);
+      atomicAdd(dst + nd * 8 + lane * 2 + 1, acc[nd][1]);
+    }
+  }
+}
+// ... or X = packed bf16 accumulator fragments v0 (rows 0-7) / v1 (rows 8-15) of each 8-column step: movmatrix turns
+// them into the B operand (k = row, n = column) without leaving the registers.
+__device__ __forceinline__ void colsum_frags(const uint32_t (&v0)[HD / 8], const uint32_t (&v1)[HD / 8], int lane, float* dst) {
+  const uint32_t ones[4] = {kOnesBf16x2, kOnesBf16x2, kOnesBf16x2, kOnesBf16x2};
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; ++nd) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16(acc, ones, movmatrix_trans(v0[nd]), movmatrix_trans(v1[nd]));
+    if (lane < 4) {
+      atomicAdd(dst + nd * 8 + lane * 2, acc[0]);
+      atomicAdd(dst + nd * 8 + lane * 2 + 1, acc[1]);
+    }
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
@@ -295,14 +328,28 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
   }
   if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(zero16)[threadIdx.x] = 0u;
   zero_tail_rows(smem, 4 * p.G, tile_bytes, p);
-  __syncthreads();
-  ptx::mbar_wait(smem_u32(bar), 0);
-
   const int tiles = sh.tiles;
   const int g = warp / tiles, tt = warp - g * tiles;
   const int64_t pr = pair0 + g;
   const bool live = pr < p.pairs;
   const int b = live ? (int)(pr / sh.H) : 0, h = live ? (int)(pr % sh.H) : 0;
+  // O (for delta) and the LSE come straight from global: fetch them while the TMA boxes are in flight
+  uint4 o_pre[4];
+  float lse_pre = 0.f;
+  {
+    const int i0 = tt * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (lane >> 3) + 4 * j, c = lane & 7;
+      o_pre[j] = make_uint4(0, 0, 0, 0);
+      if (live && i0 + r < sh.N)
+        o_pre[j] = *reinterpret_cast<const uint4*>(o + (((int64_t)b * sh.N + i0 + r) * sh.H + h) * HD + c * 8);
+    }
+    if (live && lane < 16 && i0 + lane < sh.N) lse_pre = lse[((int64_t)b * sh.H + h) * sh.N + i0 + lane];
+  }
+  __syncthreads();
+  ptx::mbar_wait(smem_u32(bar), 0);
+
   uint8_t* sQ = smem + g * pair_bytes;
   uint8_t* sK = sQ + tile_bytes;    // after phase A: the parked P blocks [tiles][16][32], then the dS blocks
   uint8_t* sV = sK + tile_bytes;    // after phase A: output staging
@@ -321,14 +368,13 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     const uint8_t* sdOt = sdO + (size_t)i0 * kRowBytes;
     // delta_i = dO_i . O_i: O straight from global (16-byte coalesced), dO from the resident tile
     {
-      const float* l = lse + ((int64_t)b * sh.H + h) * N;
-      if (lane < 16) sL[i0 + lane] = (i0 + lane < N) ? l[i0 + lane] * kLog2e : CUDART_INF_F;  // +inf -> P = 0
+      if (lane < 16) sL[i0 + lane] = (i0 + lane < N) ? lse_pre * kLog2e : CUDART_INF_F;  // +inf -> P = 0
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = (lane >> 3) + 4 * j, c = lane & 7;
         float part = 0.f;
         if (i0 + r < N) {
-          const uint4 ov = *reinterpret_cast<const uint4*>(o + (((int64_t)b * N + i0 + r) * sh.H + h) * HD + c * 8);
+          const uint4 ov = o_pre[j];
           const uint4 dv4 = *reinterpret_cast<const uint4*>(sdOt + tile_off<HD>(r, c));
           part = bf16x2_dot(ov.x, dv4.x) + bf16x2_dot(ov.y, dv4.y) + bf16x2_dot(ov.z, dv4.z) + bf16x2_dot(ov.w, dv4.w);
         }
@@ -379,8 +425,17 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     }
     // dQ leaves from the accumulator fragments (the Q rows are operands of the neighbours' phase B): a quad writes
     // 16 contiguous bytes, two n-steps complete a 32-byte sector in L2
-    __nv_bfloat16* dq0 = dq + base + (int64_t)(i0 + r0) * sh.sn;
-    store_frag<HD>(acc, sh.scale, dq0, dq0 + 8 * sh.sn, ok0, ok1, sh.colsum ? sh.colsum + h * HD : nullptr, lane);
+    __nv_bfloat16* dq0 = dq + base + (int64_t)(i0 + r0) * sh.sn + (lane & 3) * 2;
+    __nv_bfloat16* dq1 = dq0 + 8 * sh.sn;
+    uint32_t v0[HD / 8], v1[HD / 8];
+#pragma unroll
+    for (int nd = 0; nd < HD / 8; ++nd) {
+      v0[nd] = ok0 ? pack_bf16x2(acc[nd][0] * sh.scale, acc[nd][1] * sh.scale) : 0u;  // rows past N: exact zeros
+      v1[nd] = ok1 ? pack_bf16x2(acc[nd][2] * sh.scale, acc[nd][3] * sh.scale) : 0u;
+      if (ok0) *reinterpret_cast<uint32_t*>(dq0 + nd * 8) = v0[nd];
+      if (ok1) *reinterpret_cast<uint32_t*>(dq1 + nd * 8) = v1[nd];
+    }
+    if (sh.colsum) colsum_frags(v0, v1, lane, sh.colsum + h * HD);  // the q rows of the qkv bias gradient
   }
   __syncthreads();  // nobody reads K / V band rows any more
   if (live) {       // park P in the K tile's first half, dS in its second half
@@ -477,7 +532,7 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
       __syncwarp();
       __nv_bfloat16* dst = pass == 0 ? dv : dk;
       store_rows<HD>(stage, lane, [&](int r) { return (j0 + r < N) ? dst + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
-      if (sh.colsum) tile_colsum<HD>(stage, lane, sh.colsum + ((pass == 0 ? 2 : 1) * sh.H + h) * HD);
+      if (sh.colsum) colsum_staged(stage, lane, sh.colsum + ((pass == 0 ? 2 : 1) * sh.H + h) * HD);
     }
   }
 }
