@@ -35,6 +35,7 @@ struct SeqParams {
   int rows_box;    // rows per TMA box (multiple of 8, <= 256)
   int nbox;        // boxes per operand
   int64_t pairs;   // B * H
+  int cs_shared;   // backward: column sums through the CTA's shared-memory accumulator (few heads: few, hot addresses)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
@@ -272,9 +273,20 @@ __device__ __forceinline__ void mma_rows(const uint32_t (&a)[4], const uint8_t* 
   }
 }
 
+// Column-sum accumulation, two adjacent columns at a time.  shared: the CTA's accumulator (fp32 shared-memory adds are
+// CAS loops in SASS: cheap only while few warps meet); global: one 8-byte vector reduction per pair.
+__device__ __forceinline__ void add_pair(float* dst, float a, float b, bool shared) {
+  if (shared) {
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(dst)), "f"(a) : "memory");
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(dst + 1)), "f"(b) : "memory");
+  } else {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(b) : "memory");
+  }
+}
+
 // Column sums on the tensor pipe: ones(16 x 16) . X(16 x 64) leaves the 64 sums in every row of the accumulator; lanes
-// 0-3 (row 0) add them to dst.  X = a staged tile (bf16 rows in shared memory) ...
-__device__ __forceinline__ void colsum_staged(const uint8_t* stage, int lane, float* dst) {
+// 0-3 (row 0) add them to dst (shared memory).  X = a staged tile (bf16 rows in shared memory) ...
+__device__ __forceinline__ void colsum_staged(const uint8_t* stage, int lane, float* dst, bool shared) {
   const uint32_t ones[4] = {kOnesBf16x2, kOnesBf16x2, kOnesBf16x2, kOnesBf16x2};
   float acc[HD / 8][4];
 #pragma unroll
@@ -284,24 +296,19 @@ __device__ __forceinline__ void colsum_staged(const uint8_t* stage, int lane, fl
   mma_rows(ones, stage, (lane & 7) + 8 * ((lane >> 3) & 1), lane, acc);
   if (lane < 4) {
 #pragma unroll
-    for (int nd = 0; nd < HD / 8; ++nd) {
-      atomicAdd(dst + nd * 8 + lane * 2, acc[nd][0]);
-      atomicAdd(dst + nd * 8 + lane * 2 + 1, acc[nd][1]);
-    }
+    for (int nd = 0; nd < HD / 8; ++nd) add_pair(dst + nd * 8 + lane * 2, acc[nd][0], acc[nd][1], shared);
   }
 }
 // ... or X = packed bf16 accumulator fragments v0 (rows 0-7) / v1 (rows 8-15) of each 8-column step: movmatrix turns
 // them into the B operand (k = row, n = column) without leaving the registers.
-__device__ __forceinline__ void colsum_frags(const uint32_t (&v0)[HD / 8], const uint32_t (&v1)[HD / 8], int lane, float* dst) {
+__device__ __forceinline__ void colsum_frags(const uint32_t (&v0)[HD / 8], const uint32_t (&v1)[HD / 8], int lane, float* dst,
+                                             bool shared) {
   const uint32_t ones[4] = {kOnesBf16x2, kOnesBf16x2, kOnesBf16x2, kOnesBf16x2};
 #pragma unroll
   for (int nd = 0; nd < HD / 8; ++nd) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     mma_bf16(acc, ones, movmatrix_trans(v0[nd]), movmatrix_trans(v1[nd]));
-    if (lane < 4) {
-      atomicAdd(dst + nd * 8 + lane * 2, acc[0]);
-      atomicAdd(dst + nd * 8 + lane * 2 + 1, acc[1]);
-    }
+    if (lane < 4) add_pair(dst + nd * 8 + lane * 2, acc[0], acc[1], shared);
   }
 }
 
@@ -320,6 +327,10 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
   float* sDall = sLall + p.G * p.alloc_rows;                          // [G][alloc_rows] delta
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sDall + p.G * p.alloc_rows);
   uint8_t* zero16 = reinterpret_cast<uint8_t*>(bar + 2);              // 16 zero bytes: the absent 8 x 8 blocks
+  // [G][3 * 64] column sums of dQ | dK | dV of this CTA's sequences: warps add here (shared-memory atomics), the CTA
+  // adds each column to global memory once.  With one global atomic per column per WARP, 40 000 warps queue on 2 304
+  // addresses and that queue, not HBM, sets the kernel time (measured: ~100 us of fixed cost at every size).
+  float* sCS = reinterpret_cast<float*>(zero16 + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pair0 = (int64_t)blockIdx.x * p.G;
   if (threadIdx.x == 0) {
@@ -327,6 +338,7 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     issue_loads<4>(tm, smem, pair_bytes, tile_bytes, smem_u32(bar), p, pair0);
   }
   if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(zero16)[threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < p.G * 3 * HD; i += blockDim.x) sCS[i] = 0.f;
   zero_tail_rows(smem, 4 * p.G, tile_bytes, p);
   const int tiles = sh.tiles;
   const int g = warp / tiles, tt = warp - g * tiles;
@@ -435,7 +447,8 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
       if (ok0) *reinterpret_cast<uint32_t*>(dq0 + nd * 8) = v0[nd];
       if (ok1) *reinterpret_cast<uint32_t*>(dq1 + nd * 8) = v1[nd];
     }
-    if (sh.colsum) colsum_frags(v0, v1, lane, sh.colsum + h * HD);  // the q rows of the qkv bias gradient
+    if (sh.colsum)  // the q rows of the qkv bias gradient
+      colsum_frags(v0, v1, lane, p.cs_shared ? sCS + g * 3 * HD : sh.colsum + h * HD, p.cs_shared);
   }
   __syncthreads();  // nobody reads K / V band rows any more
   if (live) {       // park P in the K tile's first half, dS in its second half
@@ -451,10 +464,9 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
     }
   }
   __syncthreads();
-  if (!live) return;
 
   // ---------------------------------------------------------------- phase B: keys t0 .. t0+15
-  {
+  if (live) {
     const int j0 = t0;
     const uint8_t* sP = sK;
     const uint8_t* sS = sK + (size_t)tiles * kBlkBytes;
@@ -532,7 +544,17 @@ __global__ void __launch_bounds__(kMaxThreads) attn_seq_bwd_kernel(
       __syncwarp();
       __nv_bfloat16* dst = pass == 0 ? dv : dk;
       store_rows<HD>(stage, lane, [&](int r) { return (j0 + r < N) ? dst + base + (int64_t)(j0 + r) * sh.sn : nullptr; });
-      if (sh.colsum) colsum_staged(stage, lane, sh.colsum + ((pass == 0 ? 2 : 1) * sh.H + h) * HD);
+      if (sh.colsum)
+        colsum_staged(stage, lane, p.cs_shared ? sCS + (g * 3 + (pass == 0 ? 2 : 1)) * HD
+                                               : sh.colsum + ((pass == 0 ? 2 : 1) * sh.H + h) * HD, p.cs_shared);
+    }
+  }
+  if (sh.colsum && p.cs_shared) {  // one global atomic per column per CTA
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.G * 3 * HD; i += blockDim.x) {
+      const int g2 = i / (3 * HD), c = i - g2 * 3 * HD;
+      const int64_t pr2 = pair0 + g2;
+      if (pr2 < p.pairs) atomicAdd(sh.colsum + ((c / HD) * sh.H + (int)(pr2 % sh.H)) * HD + (c % HD), sCS[i]);
     }
   }
 }
@@ -588,6 +610,8 @@ SeqParams make_params(int B, int H, int N, int window, float scale, int64_t sb, 
   G = std::min(G, std::max(1, (int)((100 * 1024) / per_pair)));
   G = std::min(G, 8);
   p.G = (int)std::min<int64_t>(G, p.pairs);
+  // 3*H*64 global addresses take one reduction per column per warp; measured crossover of the two schemes: H = 6 / 12
+  p.cs_shared = H <= 8 ? 1 : 0;
   return p;
 }
 
@@ -628,7 +652,7 @@ int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, con
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&tv, v, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&td, dout, B, H, N, (int64_t)N * H * HD, (int64_t)H * HD, HD, p.rows_box)) return rc;
-  const size_t smem = (size_t)p.G * (4 * p.alloc_rows * kRowBytes + 2 * p.alloc_rows * 4) + 32 + 1024;
+  const size_t smem = (size_t)p.G * (4 * p.alloc_rows * kRowBytes + 2 * p.alloc_rows * 4 + 3 * HD * 4) + 32 + 1024;
   static bool configured = false;
   if (!configured) {
     FAVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_seq_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
