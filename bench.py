@@ -273,6 +273,55 @@ def load_traffic(workload):
         return None
 
 
+def run_infer(device, steps, warmup):
+    """BASELINE configs[4]: high-resolution SPPP + MHLA inference (512 px, patch 8 -> 4096 patch tokens pooled to 64
+    superpixel tokens), 32 images per GPU (the per-GPU share of a batch of 256 on 8 GPUs; no communication).  Forward
+    only, eval mode, bf16 autocast, captured in a CUDA graph; inputs resident in HBM, two alternating batches."""
+    from favit_b200 import synth
+    from favit_b200.models import SPPPViTMHLA
+    cfg = dict(img=512, ps=8, D=384, depth=12, H=6, K=64, W=7, B=32)
+    torch.manual_seed(1234)
+    m = SPPPViTMHLA(img_size=cfg["img"], patch_size=cfg["ps"], num_classes=1000, embed_dim=cfg["D"], depth=cfg["depth"],
+                    num_heads=cfg["H"], num_superpixels=cfg["K"], window_size=cfg["W"], use_mhla=True,
+                    pooling_type="mean").to(device).eval()
+    m.validate_slots = False
+    batches = []
+    for i in range(2):
+        x = synth.images(cfg["B"], cfg["img"], seed=4321 + i, device=device)
+        maps = synth.voronoi_label_maps(cfg["B"], cfg["img"], cfg["K"], seed=4321 + i, device=device, exact_k=True,
+                                        patch_size=cfg["ps"])
+        batches.append((x, maps))
+
+    def fwd(x, maps):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return m(x, maps)
+
+    for i in range(3):
+        fwd(*batches[i % 2])
+    torch.cuda.synchronize(device)
+    sx, smaps = batches[0][0].clone(), batches[0][1].clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fwd(sx, smaps)
+
+    def step(i):
+        x, maps = batches[i % 2]
+        sx.copy_(x, non_blocking=True)
+        smaps.copy_(maps, non_blocking=True)
+        g.replay()
+        return out
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    ms = timed_steps(step, steps, False, device) / steps
+    return {"value": round(cfg["B"] / (ms / 1e3), 1), "unit": "images/s, forward only (eval, no_grad)",
+            "ms_per_step": round(ms, 3), "steps": steps,
+            "config": {"workload": "sppp_vits_mhla_512_infer", "per_gpu_batch": cfg["B"], "img": cfg["img"],
+                       "patch": cfg["ps"], "patch_tokens": (cfg["img"] // cfg["ps"]) ** 2, "superpixels": cfg["K"],
+                       "embed_dim": cfg["D"], "depth": cfg["depth"], "heads": cfg["H"], "window": cfg["W"],
+                       "cuda_graph": True, "dtype": "bf16"}}
+
+
 def run_favit(args, wl, rank, world, local_rank):
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -451,6 +500,8 @@ def main():
         o2 = run_favit(args2, WORKLOADS[args2.workload], rank, world, local_rank)
         out["also"] = {args2.workload: {k: o2[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches",
                                                            "config", "kernel_families")}}
+        # BASELINE configs[4] (high-resolution SPPP + MHLA inference, the per-GPU share of the 8-GPU batch)
+        out["also"]["sppp_vits_mhla_512_infer"] = run_infer(torch.device("cuda", local_rank), 20, 3)
     if rank == 0:
         print(json.dumps(out), flush=True)
 

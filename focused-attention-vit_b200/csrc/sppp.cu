@@ -506,6 +506,81 @@ __global__ void __launch_bounds__(1024) sppp_slot_smem_kernel(const int64_t* __r
   }
 }
 
+// ---- superpixel centroids -----------------------------------------------------------------------------------
+// models/sppp_mhla.py:226-262: for every image and every label s in [0, K) the mean of x / W and y / H over the
+// pixels carrying s ((0.5, 0.5) for a label without pixels).  The reference loops over images and labels with a
+// device sync per `if mask.sum() > 0`; a batched index_add_ is atomics-bound (1.2 ms per call at 32 x 512 x 512).
+// Here each thread walks 8 consecutive pixels of one row (two-label 16-byte loads) and flushes a (count, sum x, y * count)
+// triple per run of equal labels into the CTA's integer accumulators in shared memory (native integer atomics, exact and
+// order-independent), CTAs add their partial sums to 64-bit global accumulators, a second tiny kernel divides.
+constexpr int kCentPix = 8;  // pixels per thread
+__global__ void __launch_bounds__(256) sppp_centroid_acc_kernel(const int64_t* __restrict__ labels, int B, int img_h,
+                                                                int img_w, int K, int rows_per_cta, int chunks,
+                                                                unsigned long long* __restrict__ acc) {
+  extern __shared__ unsigned int s_cent[];  // [3][K]: count, sum x, sum y (< 2^32 per CTA: <= 32768 pixels, coordinates < 65536)
+  const int b = blockIdx.x / chunks, ch = blockIdx.x - b * chunks;
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_cent[i] = 0;
+  __syncthreads();
+  const int y0 = ch * rows_per_cta, y1 = min(img_h, y0 + rows_per_cta);
+  const int groups = (img_w + kCentPix - 1) / kCentPix;  // 8-pixel groups per row
+  const bool vec = (img_w % 2 == 0) && ((uintptr_t)labels % 16 == 0);
+  for (int i = threadIdx.x; i < (y1 - y0) * groups; i += blockDim.x) {
+    const int y = y0 + i / groups, x0 = (i % groups) * kCentPix;
+    const int64_t* src = labels + ((int64_t)b * img_h + y) * img_w + x0;
+    long long v[kCentPix];
+    if (vec && x0 + kCentPix <= img_w) {
+#pragma unroll
+      for (int k = 0; k < kCentPix / 2; ++k) {
+        const longlong2 t = __ldcs(reinterpret_cast<const longlong2*>(src) + k);
+        v[2 * k] = t.x;
+        v[2 * k + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kCentPix; ++k) v[k] = (x0 + k < img_w) ? src[k] : -1;
+    }
+    long long cur = v[0];
+    int n = 0, sx = 0;
+#pragma unroll
+    for (int k = 0; k <= kCentPix; ++k) {
+      const long long l = k < kCentPix ? v[k] : cur - 1;  // sentinel: flush the last run
+      if (k == kCentPix || l != cur) {
+        if (n > 0 && cur >= 0 && cur < K) {
+          atomicAdd(&s_cent[(int)cur], (unsigned)n);
+          atomicAdd(&s_cent[K + (int)cur], (unsigned)sx);
+          atomicAdd(&s_cent[2 * K + (int)cur], (unsigned)(n * y));
+        }
+        cur = l;
+        n = 0;
+        sx = 0;
+      }
+      if (k < kCentPix) {
+        ++n;
+        sx += x0 + k;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x)
+    if (s_cent[i]) atomicAdd(acc + (int64_t)b * 3 * K + i, (unsigned long long)s_cent[i]);
+}
+
+__global__ void __launch_bounds__(256) sppp_centroid_fin_kernel(const unsigned long long* __restrict__ acc, int B, int K,
+                                                                int img_h, int img_w, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K, k = i - b * K;
+  const unsigned long long n = acc[(int64_t)b * 3 * K + k];
+  float cx = 0.5f, cy = 0.5f;
+  if (n > 0) {
+    cx = (float)((double)acc[(int64_t)b * 3 * K + K + k] / (double)n / (double)img_w);
+    cy = (float)((double)acc[(int64_t)b * 3 * K + 2 * K + k] / (double)n / (double)img_h);
+  }
+  out[2 * i] = cx;
+  out[2 * i + 1] = cy;
+}
+
+
 // ---- pool forward: TMA-staged tiles ------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1100,6 +1175,30 @@ extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int im
   } else {
     sppp_slot_kernel<1024><<<B, 1024, 0, st>>>(dom, slot, num_slots, counts, slot_label, offsets, order, P, r_cap);
   }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+extern "C" int favit_sppp_centroids(const int64_t* labels, int B, int img_h, int img_w, int K, unsigned long long* acc,
+                                    float* centroids, favit_stream stream) {
+  FAVIT_CHECK_ARG(labels && acc && centroids, "sppp_centroids: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && img_h > 0 && img_w > 0 && K > 0, "sppp_centroids: sizes must be > 0");
+  FAVIT_CHECK_ARG(K <= 4096, "sppp_centroids: K = %d > 4096 unsupported", K);
+  FAVIT_CHECK_ARG((int64_t)img_h * img_w * (int64_t)(img_w + img_h) < ((int64_t)1 << 62), "sppp_centroids: image too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  FAVIT_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * 3 * K * sizeof(unsigned long long), st));
+  // per-CTA partial sums stay below 2^31: at most 32768 pixels (x, y < 65536 -> sums < 2^31) per CTA
+  FAVIT_CHECK_ARG(img_w < 65536 && img_h < 65536, "sppp_centroids: image side must be < 65536");
+  int rows = 32768 / img_w;
+  rows = rows < 1 ? 1 : rows;
+  const int want = ceil_div(8 * num_sms(), B);  // enough CTAs to fill the machine
+  rows = std::min(rows, std::max(1, ceil_div(img_h, want)));
+  const int chunks = ceil_div(img_h, rows);
+  FAVIT_CHECK_ARG((int64_t)B * chunks < INT_MAX, "sppp_centroids: grid too large");
+  sppp_centroid_acc_kernel<<<(unsigned)(B * chunks), 256, (size_t)3 * K * sizeof(unsigned), st>>>(labels, B, img_h, img_w, K,
+                                                                                          rows, chunks, acc);
+  FAVIT_CHECK_LAUNCH();
+  sppp_centroid_fin_kernel<<<(unsigned)ceil_div(B * K, 256), 256, 0, st>>>(acc, B, K, img_h, img_w, centroids);
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }

@@ -277,6 +277,9 @@ class SPPPViTMHLA(nn.Module):
         B, H, W = seg.shape
         K = self.num_superpixels
         dev = seg.device
+        if seg.is_cuda and K <= 4096:
+            from . import ops
+            return ops.sppp_centroids(seg if seg.dtype == torch.int64 else seg.to(torch.int64), K)
         valid = (seg >= 0) & (seg < K)
         idx = (torch.arange(B, device=dev).view(B, 1, 1) * K + seg.clamp(0, K - 1)).reshape(-1)
         w = valid.reshape(-1).float()

@@ -321,6 +321,29 @@ def _(labels, patch_size, img_size, r_cap):
             labels.new_empty((B, P), dtype=i32)]
 
 
+@torch.library.custom_op("favit::sppp_centroids", mutates_args=())
+def sppp_centroids(labels: Tensor, K: int) -> Tensor:
+    """labels int64 [B,H,W] -> fp32 [B,K,2] (x, y) centroids of labels 0..K-1 in normalised coordinates, (0.5, 0.5) for
+    labels without pixels (sppp_mhla.py:226-262)."""
+    _cuda(labels)
+    if labels.dtype != torch.int64 or labels.dim() != 3:
+        raise ValueError("sppp_centroids: labels must be an int64 [B,H,W] tensor")
+    labels = labels.contiguous()
+    B, Hh, Ww = labels.shape
+    out = torch.empty((B, K, 2), dtype=torch.float32, device=labels.device)
+    if B * K:
+        acc = torch.empty((B, 3, K), dtype=torch.int64, device=labels.device)
+        rc = L.call("sppp_centroids", B * Hh * Ww * 8.0 + B * K * 8.0, L.lib().favit_sppp_centroids, _p(labels), B, Hh, Ww, K,
+                    _p(acc), _p(out), _stream())
+        L.check(rc, "favit_sppp_centroids")
+    return out
+
+
+@sppp_centroids.register_fake
+def _(labels, K):
+    return labels.new_empty((labels.shape[0], K, 2), dtype=torch.float32)
+
+
 @torch.library.custom_op("favit::sppp_pool_fwd", mutates_args=())
 def sppp_pool_fwd(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int,
                   out_dtype: torch.dtype) -> Tensor:

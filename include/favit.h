@@ -193,6 +193,13 @@ int favit_sppp_assign(const int64_t* labels, int B, int img_h, int img_w, int pa
                       int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap,
                       favit_stream stream);
 
+/* Superpixel centroids for the dynamic positional encoding — replaces models/sppp_mhla.py:226-262 (a Python loop over
+ * images and labels with a device sync per label).  labels int64 [B,H,W]; centroids fp32 [B,K,2] = (mean x / W,
+ * mean y / H) of the pixels carrying label k in [0, K), (0.5, 0.5) for a label without pixels; labels outside [0, K)
+ * are ignored.  acc: workspace of B*3*K unsigned 64-bit integers (zeroed by the call): the sums are exact integers. */
+int favit_sppp_centroids(const int64_t* labels, int B, int img_h, int img_w, int K, unsigned long long* acc,
+                         float* centroids, favit_stream stream);
+
 /* SuperpixelPooling.pool('mean') — replaces models/sppp.py:192-223 + the per-image loop/stack at
  * models/sppp_mhla.py:286-300.  x[B,P,D] (x_dtype) -> out[B,R,D] (out_dtype; the reference always
  * produces fp32, sppp.py:198).  Rows r >= num_slots[b] are zero-filled. */

@@ -155,3 +155,26 @@ def test_unequal_slot_counts_raise():
         SuperpixelPooling("mean").pool_batch(x, a, 2)
     with pytest.raises(ValueError):
         SuperpixelPooling("median").pool(x[0], {0: [0]})
+
+
+@pytest.mark.parametrize("B,H,W,K", [(3, 32, 32, 4), (2, 224, 224, 16), (2, 37, 53, 9), (1, 512, 512, 64), (2, 64, 48, 300)])
+def test_centroids_match_reference_loop(B, H, W, K):
+    """favit::sppp_centroids against the reference's per-image / per-label loop (sppp_mhla.py:236-262) restated in fp64:
+    labels outside [0, K) are ignored, labels without pixels give (0.5, 0.5)."""
+    from favit_b200 import ops
+    rng = np.random.default_rng(B * 1000 + H + K)
+    lm = rng.integers(-2, K + 3, size=(B, H, W)).astype(np.int64)
+    lm[:, : H // 2, : W // 2] = rng.integers(0, max(K // 2, 1), size=(B, 1, 1))   # large uniform regions (long runs)
+    if K > 3:
+        lm[lm == K - 1] = 0                                                       # a label that never occurs
+    ref = np.full((B, K, 2), 0.5)
+    ys, xs = np.meshgrid(np.arange(H) / H, np.arange(W) / W, indexing="ij")
+    for b in range(B):
+        for s in range(K):
+            m = lm[b] == s
+            if m.any():
+                ref[b, s, 0] = xs[m].mean()
+                ref[b, s, 1] = ys[m].mean()
+    got = ops.sppp_centroids(torch.from_numpy(lm).cuda(), K)
+    assert got.dtype == torch.float32 and got.shape == (B, K, 2)
+    assert np.abs(got.cpu().numpy() - ref).max() < 1e-6
