@@ -66,7 +66,8 @@ def _(x, ln1_w, ln1_b, wqkv, bqkv, wproj, bproj, ln2_w, ln2_b, w1, b1, w2, b2, B
 def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, ln2_w: Tensor, w1: Tensor, w2: Tensor,
               xn: Tensor, mu1: Tensor, rs1: Tensor, qkv: Tensor, o: Tensor, lse: Tensor, x2: Tensor, xn2: Tensor,
               mu2: Tensor, rs2: Tensor, hpre: Tensor, h: Tensor, B: int, N: int, H: int, window: int) -> List[Tensor]:
-    """Returns [dx, dln1_w, dln1_b, dwqkv, dbqkv, dwproj, dbproj, dln2_w, dln2_b, dw1, db1, dw2, db2] (all fp32)."""
+    """Returns [dx, small, dwqkv, dwproj, dw1, dw2, db2] (all fp32); `small` packs every small gradient of the block in
+    one buffer (custom-op outputs may not alias each other): see `unpack_block_grads`."""
     M, D = x.shape
     cd = wqkv.dtype
     hd = D // H
@@ -79,23 +80,41 @@ def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, 
         g_c, gsum = handed
     else:
         g_c, gsum = (g.to(cd) if bf else g), None
+    # every small accumulator of this backward (bias-gradient column sums, LayerNorm dgamma / dbeta) lives in one zeroed
+    # buffer: one fill launch per block instead of four
+    Hd = w2.shape[1]
+    z = torch.zeros((Hd + 9 * D,), dtype=torch.float32, device=x.device)
+    z_db1, z_ln2, z_attn, z_ln1 = z[:Hd], z[Hd:Hd + 3 * D].view(3, D), z[Hd + 3 * D:Hd + 6 * D], z[Hd + 6 * D:].view(3, D)
     dw2, db2 = raw.linear_wgrad(g_c, h, want_bias=gsum is None)
     if gsum is not None:
         db2 = gsum
-    dhpre, db1 = raw.linear_dgrad(g_c, w2, hpre, cd, colsum=True)   # fc1's bias gradient from the GELU' epilogue
+    dhpre, db1 = raw.linear_dgrad(g_c, w2, hpre, cd, colsum=True, zeroed=z_db1)   # fc1's bias gradient (GELU' epilogue)
     dw1, _ = raw.linear_wgrad(dhpre, xn2, want_bias=False)
     dxn2 = raw.linear_dgrad(dhpre, w1, None, cd)
-    g2, g2_b, dg2, dbt2, dbp = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf)   # dbp = column sums of g2
+    g2, g2_b, dg2, dbt2, dbp = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf, zeroed=z_ln2)   # dbp = column sums of g2
     g2_c = g2_b if bf else g2
     dwp, _ = raw.linear_wgrad(g2_c, o, want_bias=False)
     do = raw.linear_dgrad(g2_c, wproj, None, cd)
-    dqkv, dbq = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window)   # qkv bias gradient from the attention backward
+    dqkv, dbq = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window, zeroed=z_attn)   # qkv bias gradient on the way
     dwq, _ = raw.linear_wgrad(dqkv, xn, want_bias=False)
     dxn = raw.linear_dgrad(dqkv, wqkv, None, cd)
-    g0, g0_b, dg1, dbt1, g0sum = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf)
+    g0, g0_b, dg1, dbt1, g0sum = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf, zeroed=z_ln1)
     _GRAD_BF16.clear()                          # at most one hand-over is alive
     _GRAD_BF16[(g0.data_ptr(), M, D)] = (g0_b if bf else g0, g0sum)
-    return [g0, dg1, dbt1, dwq, dbq, dwp, dbp, dg2, dbt2, dw1, db1, dw2, db2]
+    # db2 is either the wgrad's own output or the column sums handed over by the block above (a slice of THAT block's
+    # buffer): a private copy keeps this op's outputs free of aliases
+    return [g0, z, dwq, dwp, dw1, dw2, db2.clone() if gsum is not None else db2]
+
+
+def unpack_block_grads(outs, D: int, Hd: int):
+    """block_bwd outputs -> (dx, dln1_w, dln1_b, dwqkv, dbqkv, dwproj, dbproj, dln2_w, dln2_b, dw1, db1, dw2, db2).
+    Layout of `small`: [db1 (Hd) | dln2_w, dln2_b, dbproj (3 x D) | dbqkv (3D) | dln1_w, dln1_b, column sums of dx (3 x D)]."""
+    g0, z, dwq, dwp, dw1, dw2, db2 = outs
+    db1 = z[:Hd]
+    ln2 = z[Hd:Hd + 3 * D].view(3, D)
+    dbq = z[Hd + 3 * D:Hd + 6 * D]
+    ln1 = z[Hd + 6 * D:].view(3, D)
+    return g0, ln1[0], ln1[1], dwq, dbq, dwp, ln2[2], ln2[0], ln2[1], dw1, db1, dw2, db2
 
 
 @block_bwd.register_fake
@@ -104,7 +123,7 @@ def _(g, x, ln1_w, wqkv, wproj, ln2_w, w1, w2, xn, mu1, rs1, qkv, o, lse, x2, xn
     e = lambda t: t.new_empty(t.shape, dtype=f32)
     D = x.shape[1]
     v = lambda n: x.new_empty((n,), dtype=f32)
-    return [e(x), v(D), v(D), e(wqkv), v(wqkv.shape[0]), e(wproj), v(D), v(D), v(D), e(w1), v(w1.shape[0]), e(w2), v(D)]
+    return [e(x), v(w2.shape[1] + 9 * D), e(wqkv), e(wproj), e(w1), e(w2), v(D)]
 
 
 @torch.library.custom_op("favit::latent_fold_fwd", mutates_args=())
@@ -165,8 +184,8 @@ class FusedBlockFn(torch.autograd.Function):
         if g2d.dtype != torch.float32:
             g2d = g2d.float()
         f = lambda t: t.detach().float().contiguous()
-        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = block_bwd(
-            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window)
+        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = unpack_block_grads(block_bwd(
+            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window), D, w2_c.shape[1])
         # gradients of the folded qkv / proj weights -> qkv.weight, qkv.bias, proj.weight (in place) + latent_proj
         dlw, dlb = latent_fold_bwd(f(qkv_w), f(qkv_b), f(proj_w), f(lat_w), f(lat_b), dwq, dbq, dwp, dbp, H)
         return (dx.view(B, N, D), dln1_w, dln1_b, dwq, dbq, dwp, dbp, dlw, dlb, dln2_w, dln2_b, dw1, db1, dw2, db2,
@@ -238,8 +257,8 @@ class FusedBlockPrefoldedFn(torch.autograd.Function):
         if g2d.dtype != torch.float32:
             g2d = g2d.float()
         f = lambda t: t.detach().float().contiguous()
-        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = block_bwd(
-            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window)
+        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = unpack_block_grads(block_bwd(
+            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window), D, w2_c.shape[1])
         ctx.stash[ctx.layer] = (dwq, dbq, dwp, dbp)
         gtok = torch.zeros(1, dtype=torch.float32, device=dx.device) if ctx.has_token else None
         return (dx.view(B, N, D), gtok, dln1_w, dln1_b, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None, None,

@@ -33,12 +33,14 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[
     return y, pre
 
 
-def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype, colsum: bool = False):
-    """dx = dy @ w (* gelu'(preact)); with colsum also the fp32 column sums of dx (returns (dx, sums))."""
+def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype, colsum: bool = False,
+                 zeroed: Optional[Tensor] = None):
+    """dx = dy @ w (* gelu'(preact)); with colsum also the fp32 column sums of dx (returns (dx, sums)).
+    `zeroed`: an already zeroed fp32 [K] buffer to accumulate the column sums into (saves a fill launch)."""
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
-    sums = torch.zeros((K,), dtype=torch.float32, device=dy.device) if colsum else None
+    sums = (zeroed if zeroed is not None else torch.zeros((K,), dtype=torch.float32, device=dy.device)) if colsum else None
     rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), _p(sums),
                 M, N, K, N, K, K, _DT[dy.dtype], _DT[out_dtype],
                 L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _s())
@@ -77,18 +79,21 @@ def ln_fwd(x: Tensor, gamma: Tensor, beta: Tensor, out_dtype: torch.dtype, eps: 
 
 
 def ln_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
-           want_bf16: bool):
-    """Returns (dx fp32, dx_bf16 or None, dgamma, dbeta, column sums of dx)."""
+           want_bf16: bool, zeroed: Optional[Tensor] = None):
+    """Returns (dx fp32, dx_bf16 or None, dgamma, dbeta, column sums of dx).  `zeroed`: an already zeroed fp32 [3, D]
+    buffer for the three accumulators (the results are then views of it, not copies)."""
     M, D = x.shape
     dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
     dxb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    acc = torch.zeros((3, D), dtype=torch.float32, device=x.device)
+    acc = zeroed if zeroed is not None else torch.zeros((3, D), dtype=torch.float32, device=x.device)
     dg, db, dxs = acc[0], acc[1], acc[2]
     work = float(dy.numel() * dy.element_size() + x.numel() * x.element_size() + dx.numel() * 4 +
                  (dres.numel() * 4 if dres is not None else 0) + (dxb.numel() * 2 if want_bf16 else 0))
     rc = L.call("ln_bwd", work, L.lib().favit_layernorm_bwd, _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(mean),
                 _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dxb), dg.data_ptr(), db.data_ptr(), dxs.data_ptr(), M, D, _s())
     L.check(rc, "favit_layernorm_bwd")
+    if zeroed is not None:
+        return dx, dxb, dg, db, dxs
     return dx, dxb, dg.clone(), db.clone(), dxs.clone()
 
 
@@ -105,11 +110,12 @@ def attn_fwd(qkv: Tensor, B: int, N: int, H: int, hd: int, window: int):
     return out, lse
 
 
-def attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, H: int, hd: int, window: int):
-    """Returns (dqkv, fp32 column sums of dqkv = the qkv bias gradient)."""
+def attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, H: int, hd: int, window: int,
+             zeroed: Optional[Tensor] = None):
+    """Returns (dqkv, fp32 column sums of dqkv = the qkv bias gradient).  `zeroed`: an already zeroed fp32 [3*H*hd]."""
     es = qkv.element_size()
     dqkv = torch.empty_like(qkv)
-    sums = torch.zeros((3 * H * hd,), dtype=torch.float32, device=qkv.device)
+    sums = zeroed if zeroed is not None else torch.zeros((3 * H * hd,), dtype=torch.float32, device=qkv.device)
     delta = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     off = H * hd * es
