@@ -30,19 +30,27 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// coefficients already multiplied by -log2(e): exp(-k) = 2^(x * poly(x^2))
+// coefficients already multiplied by -log2(e): exp(-k(x)) = 2^(x * poly(x^2)),  Phi(x) ~= sigma(k(x))
 __device__ __forceinline__ float phi_fast(float x) {
-  x = fminf(fmaxf(x, -8.f), 8.f);  // the fit is monotone on [-8, 8]; Phi(+-8) is 0 / 1 to 6e-16
-  const float x2 = x * x;
+  // the fit is monotone on [-8, 8]; clamping x^2 (one instruction) keeps the exponent monotone beyond: Phi -> 0 / 1
+  const float x2 = fminf(x * x, 64.f);
   float p = fmaf(1.0319492e-3f, x2, -1.0688557e-1f);
   p = fmaf(p, x2, -2.3009992f);
   return rcp_approx(1.f + ex2_approx(p * x));
 }
 __device__ __forceinline__ float gelu_fast(float x) { return x * phi_fast(x); }
+// gelu'(x) = Phi(x) + x * phi(x).  With Phi = sigma(k(x)) the density is Phi' = Phi (1 - Phi) k'(x): the exact
+// derivative of gelu_fast, one exponential instead of two (the epilogue is SFU-bound: 3 -> 2 MUFU per element);
+// |error| vs the erf form <= 1.2e-4.  k'(x) = -ln 2 * (5 c5 x^4 + 3 c3 x^2 + c1).
 __device__ __forceinline__ float dgelu_fast(float x) {
-  // Phi(x) + x * phi(x),  phi(x) = exp(-x^2 / 2) / sqrt(2 pi)
-  const float pdf = ex2_approx(x * x * -0.72134752f);  // underflows to 0 for |x| > 13: x * pdf stays finite
-  return fmaf(x * 0.3989422804014327f, pdf, phi_fast(x));
+  const float x2 = fminf(x * x, 64.f);
+  float p = fmaf(1.0319492e-3f, x2, -1.0688557e-1f);
+  p = fmaf(p, x2, -2.3009992f);
+  const float P = rcp_approx(1.f + ex2_approx(p * x));
+  float kp = fmaf(-3.5764635e-3f, x2, 2.2226212e-1f);
+  kp = fmaf(kp, x2, 1.5949311f);
+  const float t = fmaf(-P, P, P);  // Phi (1 - Phi): 0 in both tails, where the clamped k' no longer matters
+  return fmaf(x * kp, t, P);
 }
 
 }  // namespace favit
