@@ -277,24 +277,36 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           if (lane == 0) tma_store_commit();
           obuf = (obuf + 1) % NOUT;
         } else if (p.act == FAVIT_EPI_GELU) {
-          // two bf16 outputs per 64-column unit: buffer 0 = pre-activation, buffer 1 = activation
+          // two bf16 outputs per 64-column unit: buffer 0 = pre-activation, buffer 1 = activation.  Each has its own
+          // bulk group, so the pre-activation store of this unit runs under its GELU arithmetic and the wait for the
+          // previous unit's activation store comes after the first half's arithmetic instead of before any of it.
           if ((c & 1) == 0) {
-            if (lane == 0) tma_store_wait_read<0>();
+            if (lane == 0) tma_store_wait_read<1>();  // the previous unit's pre-activation store has read buffer 0
             __syncwarp();
           }
           stage_bf16(outbuf, lane, (c & 1) * 4, v);
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (col - 32 < p.N) tma_store_2d(&tmC2, outbuf_u32, col - 32, row0);
+              tma_store_commit();
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read<0>();  // ... and its activation store has read buffer 1
+            __syncwarp();
+          }
           stage_bf16(outbuf + (NOUT - 1) * kUnit, lane, (c & 1) * 4, v);
           if (c & 1) {
             fence_proxy_async_smem();
             __syncwarp();
-            const int ucol = col - 32;
-            if (lane == 0 && ucol < p.N) {
-              tma_store_2d(&tmC2, outbuf_u32, ucol, row0);
-              tma_store_2d(&tmC, outbuf_u32 + (NOUT - 1) * kUnit, ucol, row0);
+            if (lane == 0) {
+              if (col - 32 < p.N) tma_store_2d(&tmC, outbuf_u32 + (NOUT - 1) * kUnit, col - 32, row0);
+              tma_store_commit();
             }
-            if (lane == 0) tma_store_commit();
           }
         } else {
           if (AUX) {  // v *= gelu'(pre-activation)
@@ -338,8 +350,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(tempty_bar(acc), 0);
+        if (leader) mbar_arrive_relaxed(tempty_bar(acc));
+        else mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

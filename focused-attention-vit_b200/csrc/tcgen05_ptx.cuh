@@ -28,6 +28,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       ::"r"(bar), "r"(cta)
       : "memory");
 }
+// Relaxed arrivals for "this TMEM accumulator has been read": the data hand-over is ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync, no generic-proxy memory is published, so the release fence of the default form
+// (MEMBAR.ALL.CTA + ERRBAR, and an L1 invalidate at cluster scope) buys nothing: it was 10 % of the epilogue's samples.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [r];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
