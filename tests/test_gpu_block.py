@@ -93,3 +93,33 @@ def test_fused_and_unfused_paths_agree():
     mask = torch.ones(2, 33, 33, device="cuda")      # an all-ones mask forces the unfused path
     y_unfused = blk(x, mask)
     assert_close(y_unfused, y_fused, torch.float32, "fused vs unfused")
+
+
+def test_batched_latent_fold_matches_per_layer_fold():
+    """favit_latent_fold_{fwd,bwd}_batched (one launch set for all blocks) against the single-layer entry points."""
+    from favit_b200 import raw
+    torch.manual_seed(7)
+    L, H, hd = 5, 3, 64
+    D = H * hd
+    dev = "cuda"
+    layers = [(torch.randn(3 * D, D, device=dev) * 0.05, torch.randn(3 * D, device=dev) * 0.1,
+               torch.randn(D, D, device=dev) * 0.05, torch.randn(D, device=dev) * 0.1,
+               torch.eye(hd, device=dev) + torch.randn(hd, hd, device=dev) * 0.05, torch.randn(hd, device=dev) * 0.1)
+              for _ in range(L)]
+    for cd in (torch.bfloat16, torch.float32):
+        batched = raw.fold_fwd_batched(layers, H, cd)
+        for lay, got in zip(layers, batched):
+            ref = raw.fold_fwd(*lay, H, cd)
+            for g, r in zip(got, ref):
+                assert g.dtype == r.dtype and torch.equal(g, r)
+    grads = [(torch.randn(3 * D, D, device=dev), torch.randn(3 * D, device=dev), torch.randn(D, D, device=dev),
+              torch.randn(D, device=dev)) for _ in range(L)]
+    ref_in = [tuple(t.clone() for t in g) for g in grads]
+    bl = [(q, qb, p, lw, lb) for (q, qb, p, pb, lw, lb) in layers]
+    dl = raw.fold_bwd_batched(bl, grads, H)
+    for i in range(L):
+        dlw, dlb = raw.fold_bwd(*bl[i], *ref_in[i], H)
+        # dlat is accumulated with floating-point atomics: order-dependent in the last bits
+        assert torch.allclose(dl[i][0], dlw, rtol=1e-5, atol=1e-4) and torch.allclose(dl[i][1], dlb, rtol=1e-5, atol=1e-4)
+        for g, r in zip(grads[i][:3], ref_in[i][:3]):    # rewritten in place by both
+            assert torch.equal(g, r)
