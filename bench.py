@@ -179,7 +179,11 @@ def run_reference_arm(args, wl, rank):
         "impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_step": B, "device": "cpu"},
+        # the favit arm's config; each timed step is a bounded sample of it (B images instead of the per-GPU batch)
+        "config": {"workload": args.workload, "global_batch": wl["B"] * max(args.gpus, 1), "per_gpu_batch": wl["B"],
+                   "img": wl["img"], "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"],
+                   "window": wl["W"], "superpixels": wl.get("K"), "sample_batch_per_step": B, "device": "cpu",
+                   "optimizer": "adamw in step"},
         "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
