@@ -110,8 +110,8 @@ def test_batched_latent_fold_matches_per_layer_fold():
         batched = raw.fold_fwd_batched(layers, H, cd)
         for lay, got in zip(layers, batched):
             ref = raw.fold_fwd(*lay, H, cd)
-            for g, r in zip(got, ref):
-                assert g.dtype == r.dtype and torch.equal(g, r)
+            for g, r in zip(got, ref):   # the folded proj bias is summed over heads with fp32 atomics: last-bit order effects
+                assert g.dtype == r.dtype and torch.allclose(g.float(), r.float(), rtol=1e-6, atol=1e-6)
     grads = [(torch.randn(3 * D, D, device=dev), torch.randn(3 * D, device=dev), torch.randn(D, D, device=dev),
               torch.randn(D, device=dev)) for _ in range(L)]
     ref_in = [tuple(t.clone() for t in g) for g in grads]
