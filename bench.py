@@ -395,7 +395,8 @@ def run_favit(args, wl, rank, world, local_rank):
     g_work, g_ms, g_n = (sum(v[0] for v in gemm), sum(v[1] for v in gemm), sum(v[2] for v in gemm)) if gemm else (0, 1, 0)
     achieved = g_work / (g_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "gemm_bf16_tcgen05_kernel (MHLA qkv/proj fwd+dgrad+wgrad launches of the timed region)",
+        "kernel": "gemm_bf16_tcgen05_2cta_kernel / gemm_bf16_tcgen05_kernel: every GEMM launch of the timed region "
+                  "(MHLA qkv / proj and the block's fc1 / fc2; forward, dgrad, wgrad)",
         "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
         "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None, "peak_source": peaks["source"] + " (sustained)",
         "launches": g_n, "share_of_step": round(g_ms / ms_total, 4),
