@@ -44,6 +44,9 @@ struct AttnShape {
   int64_t sb, sn, sh;  // q/k/v strides in elements
   float scale_log2;    // scale * log2(e)
   float scale;
+  float drop_p = 0.f;      // attention-probability dropout (mhla.py:147); 0 = off
+  float inv_keep = 1.f;    // 1 / (1 - drop_p)
+  uint64_t seed = 0;
 };
 
 struct WindowRow {
@@ -63,6 +66,33 @@ __device__ __forceinline__ WindowRow window_row(int i, int N, int W) {
 // multiplicity of key j in query i's window
 __device__ __forceinline__ int window_mult(const WindowRow& r, int j) {
   return ((j >= r.s && j < r.e) ? 1 : 0) + ((j == r.tgt) ? r.pad : 0);
+}
+
+// ---- attention-probability dropout (mhla.py:147, nn.Dropout on the softmax output [B,H,N,W]) ---------------------
+// The reference draws one Bernoulli per WINDOW SLOT, so the pad copies of an edge key are dropped independently.  Slot
+// `pos` of row (b, h, i) is kept iff a counter-based hash of (seed, ((b*H + h)*N + i)*W + pos) gives u >= p (splitmix64
+// finaliser, 24-bit uniform): stateless, so forward, the dQ pass and the dK/dV pass regenerate the same mask, and the
+// CPU oracle reproduces it bit for bit.  Slot order is the reference's (mhla.py:72-79): s == 0 rows hold the band
+// first and the copies of key N-1 after it, the other rows the copies of key 0 first.
+__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t counter, float p) {
+  uint64_t z = seed + counter * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.f / 16777216.f) >= p;
+}
+// sum over the copies of key j in row i of keep / (1 - p): replaces the multiplicity in everything downstream of the
+// softmax normaliser
+__device__ __forceinline__ float kept_weight(const AttnShape& sh, int b, int h, int i, const WindowRow& r, int j) {
+  const uint64_t row = (((uint64_t)b * sh.H + h) * sh.N + i) * (uint64_t)sh.W;
+  const int band = r.e - r.s;
+  int kept = 0;
+  if (j >= r.s && j < r.e) kept += drop_keep(sh.seed, row + (r.s == 0 ? j - r.s : r.pad + j - r.s), sh.drop_p) ? 1 : 0;
+  if (j == r.tgt) {
+    const int p0 = (r.s == 0) ? band : 0;
+    for (int t = 0; t < r.pad; ++t) kept += drop_keep(sh.seed, row + p0 + t, sh.drop_p) ? 1 : 0;
+  }
+  return (float)kept * sh.inv_keep;
 }
 
 // Sum over the LPQ consecutive lanes that own one query/key.  The shuffle names only the lanes of the
@@ -117,14 +147,17 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ q, 
   constexpr int JB = 4;
   for (int t0 = 0; t0 < cnt; t0 += JB) {
     float sc[JB];
+    float wf[JB];  // dropout: kept copies / ((1 - p) * multiplicity); 1 without dropout
     float vf[JB][8];
 #pragma unroll
     for (int u = 0; u < JB; ++u) {
       const int t = t0 + u;
       sc[u] = -CUDART_INF_F;
+      wf[u] = 1.f;
       if (t < cnt) {
         const int j = (t < band) ? (r.s + t) : r.tgt;
         const int mult = (t < band) ? (1 + ((j == r.tgt) ? r.pad : 0)) : r.pad;
+        if (sh.drop_p > 0.f) wf[u] = kept_weight(sh, b, h, i, r, j) / (float)mult;
         float kf[8];
         load8(k + base + (int64_t)j * sh.sn, kf);
         load8(v + base + (int64_t)j * sh.sn, vf[u]);
@@ -150,9 +183,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ q, 
 #pragma unroll
       for (int u = 0; u < JB; ++u) {
         const float p = exp2f(sc[u] - m_new);  // -inf -> 0
-        l_run += p;
+        l_run += p;                            // the softmax normaliser never sees the dropout
+        const float pw = p * wf[u];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) acc[d] = fmaf(p, vf[u][d], acc[d]);
+        for (int d = 0; d < 8; ++d) acc[d] = fmaf(pw, vf[u][d], acc[d]);
       }
       m_run = m_new;
     }
@@ -223,7 +257,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(
     const bool keep = (mrow == nullptr) || (mrow[j] != 0);
     if (keep) {
       const float p = exp2f(dot * sh.scale_log2 + ((mult > 1) ? log2f((float)mult) : 0.f) - L2);
-      const float ds = p * (dp - dl);
+      const float wfac = sh.drop_p > 0.f ? kept_weight(sh, b, h, i, r, j) / (float)mult : 1.f;
+      const float ds = p * (wfac * dp - dl);
 #pragma unroll
       for (int d = 0; d < 8; ++d) acc[d] = fmaf(ds, kf[d], acc[d]);
     }
@@ -290,10 +325,12 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(
       dp = group_sum<LPQ>(dp, gmask);
       const float p = exp2f(dot * sh.scale_log2 + ((mult > 1) ? log2f((float)mult) : 0.f) -
                             lse_bh[i] * kLog2e);
-      const float ds = p * (dp - dl_bh[i]);
+      const float wfac = sh.drop_p > 0.f ? kept_weight(sh, b, h, i, r, j) / (float)mult : 1.f;
+      const float ds = p * (wfac * dp - dl_bh[i]);
+      const float pv = p * wfac;
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
-        dvf[d] = fmaf(p, dof[d], dvf[d]);
+        dvf[d] = fmaf(pv, dof[d], dvf[d]);
         dkf[d] = fmaf(ds, qf[d], dkf[d]);
       }
     }
@@ -353,10 +390,7 @@ int check_common(const void* q, const void* k, const void* v, int B, int H, int 
   FAVIT_CHECK_ARG(sb % al == 0 && sn % al == 0 && shh % al == 0, "mhla_attn: strides must keep 16-byte alignment");
   FAVIT_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0),
                   "mhla_attn: q/k/v must be 16-byte aligned");
-  if (dropout_p != 0.f) {
-    set_error("mhla_attn: attention-probability dropout is not implemented in this build");
-    return FAVIT_ERR_UNSUPPORTED;
-  }
+  FAVIT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "mhla_attn: dropout_p must be in [0, 1) (got %g)", (double)dropout_p);
   return FAVIT_OK;
 }
 
@@ -377,16 +411,18 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
                                    float* lse, int B, int H, int N, int hd, int window, float scale,
                                    int64_t stride_b, int64_t stride_n, int64_t stride_h, favit_dtype dtype,
                                    float dropout_p, uint64_t seed, favit_stream stream) {
-  (void)seed;
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse, "mhla_attn_fwd: null out/lse");
-  if (attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) && ((uintptr_t)out % 16) == 0)
+  const bool drop = dropout_p > 0.f;  // dropout (training, non-default) runs on the general kernels
+  if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
+      ((uintptr_t)out % 16) == 0)
     return attn_seq_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
-  if (attn_mma_applicable(hd, window, dtype, mask))
+  if (!drop && attn_mma_applicable(hd, window, dtype, mask))
     return attn_mma_fwd(q, k, v, out, lse, B, H, N, hd, window, scale, stride_b, stride_n, stride_h,
                         (cudaStream_t)stream);
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
+  if (drop) { sh.drop_p = dropout_p; sh.inv_keep = 1.f / (1.f - dropout_p); sh.seed = seed; }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FAVIT_BF16) {
     FAVIT_DISPATCH_HD(__nv_bfloat16, launch_fwd, q, k, v, mask, out, lse, sh, st)
@@ -403,19 +439,20 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
                                    float scale,
                                    int64_t stride_b, int64_t stride_n, int64_t stride_h, favit_dtype dtype,
                                    float dropout_p, uint64_t seed, favit_stream stream) {
-  (void)seed;
   int rc = check_common(q, k, v, B, H, N, hd, window, stride_b, stride_n, stride_h, dtype, dropout_p);
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse && dout && dq && dk && dv && delta, "mhla_attn_bwd: null pointer");
-  if (attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
+  const bool drop = dropout_p > 0.f;
+  if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
       ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
       ((uintptr_t)dv % 16) == 0)
     return attn_seq_bwd(q, k, v, out, lse, dout, dq, dk, dv, dqkv_colsum, B, H, N, window, scale, stride_b, stride_n,
                         stride_h, (cudaStream_t)stream);
-  if (attn_mma_applicable(hd, window, dtype, mask))
+  if (!drop && attn_mma_applicable(hd, window, dtype, mask))
     return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, dqkv_colsum, B, H, N, hd, window, scale, stride_b,
                         stride_n, stride_h, (cudaStream_t)stream);
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
+  if (drop) { sh.drop_p = dropout_p; sh.inv_keep = 1.f / (1.f - dropout_p); sh.seed = seed; }
   cudaStream_t st = (cudaStream_t)stream;
   auto run = [&]() -> int {
     if (dtype == FAVIT_BF16) {

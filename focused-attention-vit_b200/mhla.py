@@ -84,10 +84,9 @@ class MultiHeadLatentAttention(nn.Module):
         if W % 2 == 0 and N > W:
             raise RuntimeError(f"stack expects each tensor to be equal size: even window_size={W} with "
                                f"seq_len={N} > window_size is ragged (reference models/mhla.py:83)")
-        if self.training and self.attn_dropout.p > 0:
-            raise NotImplementedError("attention-probability dropout (p > 0, training) is not implemented in the "
-                                      "favit kernels; construct with dropout=0.0 (the reference default)")
         cd = compute_dtype(x)
+        if self.training and self.attn_dropout.p > 0:
+            return self._forward_attn_dropout(x, attention_mask, cd)
         with torch.autocast("cuda", enabled=False):
             qw, qb, pw, pb = fold_latent(self.qkv.weight.float(), self.qkv.bias.float(), self.proj.weight.float(),
                                          self.proj.bias.float(), self.latent_proj.weight.float(),
@@ -100,6 +99,38 @@ class MultiHeadLatentAttention(nn.Module):
             out, _ = ops.mhla_attn(qkv.view(B, N, 3, self.num_heads, self.head_dim), W, mask)
             y = ops.linear(out.reshape(B * N, D), pw, pb).view(B, N, D)
         return self.proj_dropout(y)
+
+    def _forward_attn_dropout(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor], cd) -> torch.Tensor:
+        """Training with attention-probability dropout p > 0 (mhla.py:147).  The K-side fold of latent_proj stays valid
+        (its bias term is constant along the softmax axis and dropout comes after the softmax); the V-side fold does
+        not, because dropped rows of probabilities no longer sum to one, so V gets its latent projection explicitly as
+        in mhla.py:106 and proj keeps its own weights.  Statistical parity with the reference: the keep-mask comes from
+        favit's counter-based generator, one Bernoulli per window slot like nn.Dropout on the [B,H,N,W] probabilities."""
+        B, N, D = x.shape
+        H, hd, W = self.num_heads, self.head_dim, self.window_size
+        p = float(self.attn_dropout.p)
+        with torch.autocast("cuda", enabled=False):
+            qkv_w, qkv_b = self.qkv.weight.float(), self.qkv.bias.float()
+            lat_w, lat_b = self.latent_proj.weight.float(), self.latent_proj.bias.float()
+            wq = torch.matmul(lat_w.t(), qkv_w[:D].reshape(H, hd, D)).reshape(D, D)       # Wq'_h = Wl^T Wq_h
+            bq = torch.matmul(qkv_b[:D].reshape(H, hd), lat_w).reshape(D)                  # bq'_h = bq_h Wl
+            xc = x if x.dtype == cd else x.to(cd)
+            qkv = ops.linear(xc.reshape(B * N, D), torch.cat([wq, qkv_w[D:]], dim=0), torch.cat([bq, qkv_b[D:]], dim=0))
+            qkv = qkv.view(B, N, 3, H, hd)
+            v_lat = ops.linear(qkv[:, :, 2].reshape(B * N * H, hd), lat_w, lat_b).view(B, N, H, hd)
+            packed = torch.stack([qkv[:, :, 0], qkv[:, :, 1], v_lat], dim=2).contiguous()
+            mask = None
+            if attention_mask is not None:
+                mask = (attention_mask != 0).to(torch.uint8).contiguous()
+            out, _ = ops.mhla_attn(packed, W, mask, p, _dropout_seed())
+            y = ops.linear(out.reshape(B * N, D), self.proj.weight.float(), self.proj.bias.float()).view(B, N, D)
+        return self.proj_dropout(y)
+
+
+def _dropout_seed() -> int:
+    """One 62-bit seed per forward from torch's CPU generator (reproducible under torch.manual_seed).  It is a host
+    value: a captured CUDA graph would replay the same mask, so train with cuda_graph=False when p > 0."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
 class MHLATransformerBlock(nn.Module):

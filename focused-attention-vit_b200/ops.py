@@ -199,8 +199,10 @@ def _qkv_args(qkv: Tensor):
 
 
 @torch.library.custom_op("favit::mhla_attn_fwd", mutates_args=())
-def mhla_attn_fwd(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
-    """qkv [B,N,3,H,hd] -> (out [B,N,H*hd], lse fp32 [B,H,N]).  mask: uint8 [B,N,N] or None."""
+def mhla_attn_fwd(qkv: Tensor, window: int, mask: Optional[Tensor], dropout_p: float = 0.0,
+                  seed: int = 0) -> Tuple[Tensor, Tensor]:
+    """qkv [B,N,3,H,hd] -> (out [B,N,H*hd], lse fp32 [B,H,N]).  mask: uint8 [B,N,N] or None.  dropout_p > 0:
+    attention-probability dropout (mhla.py:147) with the counter-based mask of (seed, b, h, i, window slot)."""
     _cuda(qkv, mask)
     B, N, H, hd, q, k, v, sb, sn, sh = _qkv_args(qkv)
     out = torch.empty((B, N, H * hd), dtype=qkv.dtype, device=qkv.device)
@@ -210,19 +212,20 @@ def mhla_attn_fwd(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Ten
     if B * N == 0:
         return out, lse
     rc = L.call("attn_fwd", 4.0 * B * N * H * hd * qkv.element_size(), L.lib().favit_mhla_attn_fwd, q, k, v, _p(mask), _p(out), _p(lse), B, H, N, hd, window, float(hd) ** -0.5,
-                                     sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
+                                     sb, sn, sh, _dt(qkv), float(dropout_p), int(seed), _stream())
     L.check(rc, "favit_mhla_attn_fwd")
     return out, lse
 
 
 @mhla_attn_fwd.register_fake
-def _(qkv, window, mask):
+def _(qkv, window, mask, dropout_p=0.0, seed=0):
     B, N, _, H, hd = qkv.shape
     return qkv.new_empty((B, N, H * hd)), qkv.new_empty((B, H, N), dtype=torch.float32)
 
 
 @torch.library.custom_op("favit::mhla_attn_bwd", mutates_args=())
-def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: int, mask: Optional[Tensor]) -> Tensor:
+def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: int, mask: Optional[Tensor],
+                  dropout_p: float = 0.0, seed: int = 0) -> Tensor:
     """Gradient of mhla_attn_fwd w.r.t. the packed qkv: returns dqkv [B,N,3,H,hd]."""
     _cuda(qkv, out, lse, dout, mask)
     B, N, H, hd, q, k, v, sb, sn, sh = _qkv_args(qkv)
@@ -237,31 +240,33 @@ def mhla_attn_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, window: i
     dq = dqkv.data_ptr()
     rc = L.call("attn_bwd", 8.0 * B * N * H * hd * es, L.lib().favit_mhla_attn_bwd, q, k, v, _p(mask), _p(out), _p(lse), _p(dout), dq, dq + H * hd * es,
                                      dq + 2 * H * hd * es, _p(delta), None, B, H, N, hd, window, float(hd) ** -0.5,
-                                     sb, sn, sh, _dt(qkv), 0.0, 0, _stream())
+                                     sb, sn, sh, _dt(qkv), float(dropout_p), int(seed), _stream())
     L.check(rc, "favit_mhla_attn_bwd")
     return dqkv
 
 
 @mhla_attn_bwd.register_fake
-def _(qkv, out, lse, dout, window, mask):
+def _(qkv, out, lse, dout, window, mask, dropout_p=0.0, seed=0):
     return torch.empty_like(qkv)
 
 
 @torch.library.custom_op("favit::mhla_attn", mutates_args=())
-def mhla_attn(qkv: Tensor, window: int, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+def mhla_attn(qkv: Tensor, window: int, mask: Optional[Tensor], dropout_p: float = 0.0,
+              seed: int = 0) -> Tuple[Tensor, Tensor]:
     """Differentiable window attention: (out [B,N,D], lse)."""
-    return mhla_attn_fwd(qkv, window, mask)
+    return mhla_attn_fwd(qkv, window, mask, dropout_p, seed)
 
 
 @mhla_attn.register_fake
-def _(qkv, window, mask):
+def _(qkv, window, mask, dropout_p=0.0, seed=0):
     B, N, _, H, hd = qkv.shape
     return qkv.new_empty((B, N, H * hd)), qkv.new_empty((B, H, N), dtype=torch.float32)
 
 
 def _attn_setup(ctx, inputs, output):
-    qkv, window, mask = inputs
+    qkv, window, mask, dropout_p, seed = inputs
     out, lse = output
+    ctx.dropout_p, ctx.seed = dropout_p, seed
     ctx.save_for_backward(qkv, out, lse, mask if mask is not None else torch.empty(0))
     ctx.window = window
     ctx.has_mask = mask is not None
@@ -273,8 +278,9 @@ def _attn_backward(ctx, dout, dlse):
     if dlse is not None:
         raise RuntimeError("mhla_attn: gradients through the log-sum-exp output are not supported")
     if dout is None:
-        return torch.zeros_like(qkv), None, None
-    return mhla_attn_bwd(qkv, out, lse, dout, ctx.window, mask if ctx.has_mask else None), None, None
+        return torch.zeros_like(qkv), None, None, None, None
+    return (mhla_attn_bwd(qkv, out, lse, dout, ctx.window, mask if ctx.has_mask else None, ctx.dropout_p, ctx.seed),
+            None, None, None, None)
 
 
 mhla_attn.register_autograd(_attn_backward, setup_context=_attn_setup)

@@ -20,6 +20,8 @@ from .mhla_oracle import (  # noqa: F401
     mhla_forward_gather,
     mhla_forward_closed_form,
     mhla_attn_core_closed_form,
+    mhla_attn_core_gather,
+    dropout_keep_mask,
     fold_latent,
 )
 from .models_oracle import (  # noqa: F401

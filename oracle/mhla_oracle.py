@@ -101,6 +101,44 @@ def mhla_forward_gather(
 
 
 # ----------------------------------------------------------------------------------------------
+# attention-probability dropout (mhla.py:147): the keep-mask of favit's counter-based generator
+# ----------------------------------------------------------------------------------------------
+def dropout_keep_mask(B: int, H: int, N: int, W: int, p: float, seed: int) -> np.ndarray:
+    """bool [B,H,N,W]: slot `pos` of row (b,h,i) is kept iff the splitmix64 finaliser of
+    seed + (((b*H + h)*N + i)*W + pos) * 0x9E3779B97F4A7C15 gives a 24-bit uniform >= p.  The reference uses torch's
+    Philox stream, so only the DISTRIBUTION is the reference's; this function pins the kernels' mask bit for bit."""
+    c = np.arange(B * H * N * W, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + c * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return (u >= np.float32(p)).reshape(B, H, N, W)
+
+
+def mhla_attn_core_gather(q, k, v, window_size: int, attention_mask: Optional[torch.Tensor] = None,
+                          keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0) -> torch.Tensor:
+    """The attention core in the reference's own formulation (mhla.py:109-154): window gather, scaled scores, mask,
+    softmax over the W slots, dropout (`keep` [B,H,N,W] bool, scaled by 1/(1-p)), PV.  q,k,v [B,H,N,hd] -> [B,H,N,hd]."""
+    B, H, N, hd = q.shape
+    idx = torch.from_numpy(window_indices(N, window_size)).to(q.device)
+    W = idx.shape[1]
+    idx_b = idx[None, None].expand(B, H, -1, -1)
+    gidx = idx_b.unsqueeze(-1).expand(-1, -1, -1, -1, hd)
+    k_win = torch.gather(k.unsqueeze(3).expand(-1, -1, -1, W, -1), 2, gidx)
+    v_win = torch.gather(v.unsqueeze(3).expand(-1, -1, -1, W, -1), 2, gidx)
+    attn = torch.matmul(q.unsqueeze(3), k_win.transpose(-2, -1)).squeeze(3) / (hd ** 0.5)
+    if attention_mask is not None:
+        wmask = torch.gather(attention_mask.unsqueeze(1).expand(-1, H, -1, -1), 3, idx_b)
+        attn = attn.masked_fill(wmask == 0, float("-inf"))
+    attn = torch.softmax(attn, dim=-1)
+    if keep is not None:
+        attn = attn * keep.to(attn.dtype) / (1.0 - dropout_p)
+    return torch.matmul(attn.unsqueeze(3), v_win).squeeze(3)
+
+
+# ----------------------------------------------------------------------------------------------
 # closed form: banded softmax with multiplicities + folded latent projection
 # ----------------------------------------------------------------------------------------------
 def fold_latent(qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b, num_heads: int):

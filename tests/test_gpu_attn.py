@@ -108,3 +108,55 @@ def test_large_shape_properties():
     assert (out.float().abs() <= vmax * 1.01 + 1e-3).all()
     out2, _ = ops.mhla_attn(qkv[5:9].contiguous(), W, None)
     assert torch.equal(out2, out[5:9])
+
+
+@pytest.mark.parametrize("case", [(2, 3, 65, 64, 7), (1, 2, 5, 64, 7), (2, 2, 17, 64, 7), (1, 2, 40, 32, 15), (1, 1, 1, 64, 7),
+                                  (1, 2, 197, 64, 7)], ids=lambda c: "B{}H{}N{}hd{}W{}".format(*c))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_attention_dropout_matches_gather_oracle_with_the_same_mask(case, dtype):
+    """mhla.py:147: dropout on the [B,H,N,W] softmax output.  The kernels' counter-based keep-mask is reproduced on the
+    CPU (oracle.dropout_keep_mask) and fed to the reference's gather formulation: forward and gradients must agree to
+    the usual tolerance, duplicated edge slots included (each copy has its own Bernoulli)."""
+    from favit_b200 import ops
+    B, H, N, hd, W = case
+    p, seed = 0.3, 123456789 + N
+    torch.manual_seed(N * 7 + W)
+    qkv_d = torch.randn(B, N, 3, H, hd).to(dtype)
+    dout_d = torch.randn(B, N, H * hd).to(dtype)
+    keep = torch.from_numpy(oracle.dropout_keep_mask(B, H, N, W, p, seed))
+    assert 0.55 < keep.float().mean().item() < 0.85 or keep.numel() < 200
+    q64 = qkv_d.double().requires_grad_(True)
+    q, k, v = [q64[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    o_ref = oracle.mhla_attn_core_gather(q, k, v, W, None, keep, p).permute(0, 2, 1, 3).reshape(B, N, H * hd)
+    (o_ref * dout_d.double()).sum().backward()
+    qc = qkv_d.cuda().requires_grad_(True)
+    out, _ = ops.mhla_attn(qc, W, None, p, seed)
+    out.backward(dout_d.cuda())
+    assert_close(out, o_ref, dtype, "out")
+    assert_close(qc.grad, q64.grad, dtype, "dqkv", factor=2.0)
+    # a different seed gives a different mask; p = 0 is the plain path
+    out2, _ = ops.mhla_attn(qc.detach(), W, None, p, seed + 1)
+    if N > 1:
+        assert not torch.equal(out2, out.detach())
+
+
+def test_module_attention_dropout_statistics():
+    """MultiHeadLatentAttention(dropout=p).train(): E[output] over masks = the p = 0 output (inverted dropout), and the
+    module runs forward + backward (reference: one p for attention-probability and projection dropout, mhla.py:43-44)."""
+    from favit_b200.mhla import MultiHeadLatentAttention
+    torch.manual_seed(0)
+    m = MultiHeadLatentAttention(embed_dim=128, num_heads=2, window_size=7, dropout=0.25).cuda()
+    x = torch.randn(2, 33, 128, device="cuda")
+    m.eval()
+    y0 = m(x)
+    m.train()
+    m.proj_dropout.p = 0.0                       # isolate the attention-probability dropout
+    acc = torch.zeros_like(y0)
+    n = 300
+    for _ in range(n):
+        acc += m(x).detach()
+    err = (acc / n - y0).abs().max().item() / y0.abs().max().item()
+    assert err < 0.08, err
+    xg = x.clone().requires_grad_(True)
+    m(xg).sum().backward()
+    assert torch.isfinite(xg.grad).all() and m.latent_proj.weight.grad is not None
