@@ -140,35 +140,6 @@ __device__ __forceinline__ void store_rows(const uint8_t* tile, int lane, F dst_
   }
 }
 
-// accumulators [HD/8][4] * m -> bf16, written to global straight from the fragments: this thread holds rows lane/4 (p0)
-// and lane/4 + 8 (p1), columns nd*8 + (lane%4)*2 + {0,1}; a quad writes 16 contiguous bytes and two n-steps complete a
-// 32-byte sector in L2.  With colsum != nullptr the column sums of the values as stored are added to colsum[0..HD).
-template <int HD>
-__device__ __forceinline__ void store_frag(const float (&acc)[HD / 8][4], float m, __nv_bfloat16* p0, __nv_bfloat16* p1,
-                                           bool ok0, bool ok1, float* colsum, int lane) {
-  const int sub = (lane & 3) * 2;
-#pragma unroll
-  for (int nd = 0; nd < HD / 8; ++nd) {
-    const uint32_t v0 = pack_bf16x2(acc[nd][0] * m, acc[nd][1] * m);
-    const uint32_t v1 = pack_bf16x2(acc[nd][2] * m, acc[nd][3] * m);
-    if (ok0) *reinterpret_cast<uint32_t*>(p0 + nd * 8 + sub) = v0;
-    if (ok1) *reinterpret_cast<uint32_t*>(p1 + nd * 8 + sub) = v1;
-    if (colsum) {
-      float c0 = (ok0 ? __uint_as_float(v0 << 16) : 0.f) + (ok1 ? __uint_as_float(v1 << 16) : 0.f);
-      float c1 = (ok0 ? __uint_as_float(v0 & 0xffff0000u) : 0.f) + (ok1 ? __uint_as_float(v1 & 0xffff0000u) : 0.f);
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-      }
-      if (lane < 4) {
-        atomicAdd(colsum + nd * 8 + sub, c0);
-        atomicAdd(colsum + nd * 8 + sub + 1, c1);
-      }
-    }
-  }
-}
-
 // 8 x 8 b16 transpose across the warp: fragment (row lane/4, cols 2*(lane%4)+{0,1}) -> the same of the transposed matrix
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
   uint32_t y;

@@ -182,8 +182,6 @@ __global__ void __launch_bounds__(T) sppp_slot_kernel(const int64_t* __restrict_
   }
 }
 
-template <typename T> struct Vec8 { static constexpr bool ok = true; };
-
 // One warp per (image, slot, 256-element column chunk).
 template <typename TIn, typename TOut, int VEC>
 __global__ void __launch_bounds__(256) sppp_pool_fwd_kernel(const TIn* __restrict__ x,
@@ -601,15 +599,6 @@ EncodeTiledFn encode_fn() {
 
 constexpr int kSliceBytes = 128;   // bytes of one patch row per tile
 constexpr int kPoolThreads = 256;  // 16 slot lanes x 16 column groups of 8 bytes
-
-__device__ __forceinline__ int lower_bound_i32(const int* a, int lo, int hi, int key) {
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
-}
 
 template <typename TIn> struct Group8;  // the 8 bytes one thread owns of a tile row
 template <> struct Group8<__nv_bfloat16> {
