@@ -203,16 +203,22 @@ class BatchedFoldFn(torch.autograd.Function):
     all of them back to the master parameters."""
 
     @staticmethod
-    def forward(ctx, H, cd, stash, *params):
-        nl = len(params) // 6
+    def forward(ctx, H, cd, stash, nl, *tensors):
+        """tensors: 6 fold parameters per layer, then (fc1.weight, fc2.weight) per layer, whose compute-dtype copies are
+        made here as well (one cast launch for all blocks); their gradients come from the blocks, not from this node."""
+        params, mlp = tensors[:6 * nl], tensors[6 * nl:]
         f = lambda t: t.detach().float().contiguous()
         layers = [tuple(f(t) for t in params[6 * i:6 * i + 6]) for i in range(nl)]
         folded = raw.fold_fwd_batched(layers, H, cd)
         flat = [t for lay in folded for t in lay]
+        if cd == torch.bfloat16:
+            casts = raw.cast_bf16_batched(list(mlp))
+        else:
+            casts = [t.detach().contiguous() for t in mlp]
         ctx.save_for_backward(*params)
-        ctx.H, ctx.stash = H, stash
-        ctx.mark_non_differentiable(*flat)
-        return (torch.zeros(1, dtype=torch.float32, device=params[0].device), *flat)
+        ctx.H, ctx.stash, ctx.n_mlp = H, stash, len(mlp)
+        ctx.mark_non_differentiable(*flat, *casts)
+        return (torch.zeros(1, dtype=torch.float32, device=params[0].device), *flat, *casts)
 
     @staticmethod
     def backward(ctx, gtoken, *unused):
@@ -225,22 +231,20 @@ class BatchedFoldFn(torch.autograd.Function):
         out = []
         for (dwq, dbq, dwp, dbp), (dlw, dlb) in zip(grads, dl):
             out += [dwq, dbq, dwp, dbp, dlw, dlb]
-        return (None, None, None, *out)
+        return (None, None, None, None, *out, *([None] * ctx.n_mlp))
 
 
 class FusedBlockPrefoldedFn(torch.autograd.Function):
     """FusedBlockFn with the folded qkv / proj weights supplied by BatchedFoldFn (see there for `token` / `stash`)."""
 
     @staticmethod
-    def forward(ctx, x, token, ln1_w, ln1_b, ln2_w, ln2_b, w1, b1, w2, b2, wq_c, bq, wp_c, bp, layer, stash, H, window,
-                eps1, eps2, cd):
+    def forward(ctx, x, token, ln1_w, ln1_b, ln2_w, ln2_b, w1, b1, w2, b2, wq_c, bq, wp_c, bp, w1_c, w2_c, layer, stash, H,
+                window, eps1, eps2, cd):
         B, N, D = x.shape
         x2d = x.reshape(B * N, D)
         if not x2d.is_contiguous():
             x2d = x2d.contiguous()
-        c = (lambda t: t.detach().to(cd)) if cd != torch.float32 else (lambda t: t.detach().contiguous())
         f = lambda t: t.detach().float().contiguous()
-        w1_c, w2_c = c(w1), c(w2)
         outs = block_fwd(x2d.detach(), f(ln1_w), f(ln1_b), wq_c, bq, wp_c, bp, f(ln2_w), f(ln2_b), w1_c, f(b1), w2_c,
                          f(b2), B, N, H, window, eps1, eps2)
         ctx.save_for_backward(x2d, ln1_w, ln2_w, wq_c, wp_c, w1_c, w2_c, *outs[1:])
@@ -262,7 +266,7 @@ class FusedBlockPrefoldedFn(torch.autograd.Function):
         ctx.stash[ctx.layer] = (dwq, dbq, dwp, dbp)
         gtok = torch.zeros(1, dtype=torch.float32, device=dx.device) if ctx.has_token else None
         return (dx.view(B, N, D), gtok, dln1_w, dln1_b, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None, None,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 def run_blocks(blocks, x: Tensor, compute_dtype: torch.dtype) -> Tensor:
@@ -270,20 +274,23 @@ def run_blocks(blocks, x: Tensor, compute_dtype: torch.dtype) -> Tensor:
     which the caller found `fusable`: the latent fold of all blocks is one launch set per pass instead of one per block."""
     attn0 = blocks[0].attn
     H, window = attn0.num_heads, attn0.window_size
-    params = []
+    params, mlp = [], []
     for blk in blocks:
         a = blk.attn
         params += [a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, a.latent_proj.weight, a.latent_proj.bias]
-    stash = {}
-    token, *flat = BatchedFoldFn.apply(H, compute_dtype, stash, *params)
+        mlp += [blk.mlp.fc1.weight, blk.mlp.fc2.weight]
+    stash, nl = {}, len(blocks)
+    token, *flat = BatchedFoldFn.apply(H, compute_dtype, stash, nl, *params, *mlp)
     if not token.requires_grad:
         token = None
+    casts = flat[4 * nl:]
     for i, blk in enumerate(blocks):
         wq_c, bq, wp_c, bp = flat[4 * i:4 * i + 4]
         fc1, fc2 = blk.mlp.fc1, blk.mlp.fc2
         x = FusedBlockPrefoldedFn.apply(x, token if i == 0 else None, blk.norm1.weight, blk.norm1.bias, blk.norm2.weight,
-                                        blk.norm2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, wq_c, bq, wp_c, bp, i,
-                                        stash, H, window, blk.norm1.eps, blk.norm2.eps, compute_dtype)
+                                        blk.norm2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, wq_c, bq, wp_c, bp,
+                                        casts[2 * i], casts[2 * i + 1], i, stash, H, window, blk.norm1.eps, blk.norm2.eps,
+                                        compute_dtype)
     return x
 
 

@@ -142,6 +142,24 @@ def fold_fwd(qkv_w: Tensor, qkv_b: Tensor, proj_w: Tensor, proj_b: Tensor, lat_w
     return wq, bq, wp, bp
 
 
+def cast_bf16_batched(tensors):
+    """fp32 tensors -> bf16 copies, one launch for all of them (views of one flat buffer)."""
+    import ctypes as C
+    n = len(tensors)
+    srcs = [t.detach().float().contiguous() for t in tensors]
+    sizes = [t.numel() for t in srcs]
+    pad = [(s + 7) // 8 * 8 for s in sizes]                      # keep every view 16-byte aligned
+    flat = torch.empty((sum(pad),), dtype=torch.bfloat16, device=srcs[0].device)
+    outs, off = [], 0
+    for t, s, p in zip(srcs, sizes, pad):
+        outs.append(flat[off:off + s].view(t.shape))
+        off += p
+    rc = L.call("cast", 0.0, L.lib().favit_cast_bf16_batched, n, (C.c_void_p * n)(*[t.data_ptr() for t in srcs]),
+                (C.c_void_p * n)(*[o.data_ptr() for o in outs]), (C.c_int64 * n)(*sizes), _s())
+    L.check(rc, "favit_cast_bf16_batched")
+    return outs
+
+
 def fold_fwd_batched(layers, H: int, cd: torch.dtype):
     """layers: list of (qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b) fp32 tensors of the L blocks of one model.
     One call for the whole model; returns L tuples (wqkv' cd, bqkv' fp32, wproj' cd, bproj' fp32), views of four

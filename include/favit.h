@@ -118,6 +118,12 @@ int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int 
 /* out[n] += sum over the M rows of x[m,n] (x row-major with leading dimension ld): a bias gradient. */
 int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int64_t ld, favit_stream stream);
 
+/* fp32 -> bf16 copies of `count` tensors in one launch per 32 tensors: the per-step cast of the fp32 master weights of
+ * the MLP (models/vit.py:107-139 fc1 / fc2 of every block) into tcgen05 GEMM operands.  src / dst / numel are HOST
+ * arrays of device pointers / element counts. */
+int favit_cast_bf16_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
+                            favit_stream stream);
+
 /* Test / tuning hook: C[M,N] = A.B^T through the tcgen05 kernel with explicit operand storage
  * (a_mn / b_mn: 0 = reduction dimension contiguous, 1 = M/N dimension contiguous), tile width
  * (0 = auto, 64, 128, 256) and split-K factor (0 = auto).  C fp32 or bf16. */
