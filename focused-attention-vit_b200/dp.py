@@ -52,8 +52,16 @@ class GradAllReducer:
             n += p.numel()
         if cur:
             groups.append(cur)
+        # every bucket is a slice of ONE flat buffer: the overlapped mode reduces bucket by bucket as backward fills
+        # them, the deferred mode (backward replayed from a CUDA graph) reduces the whole buffer in a single call
+        # instead of paying the launch latency of a dozen collectives after the step
+        sizes = [sum(p.numel() for p in g) for g in groups]
+        starts = [0]
+        for sz in sizes:
+            starts.append(starts[-1] + (sz + 63) // 64 * 64)       # 256-byte aligned bucket starts
+        self.flat_all = torch.zeros(starts[-1], dtype=torch.float32, device=groups[0][0].device)
         for bi, g in enumerate(groups):
-            flat = torch.zeros(sum(p.numel() for p in g), dtype=torch.float32, device=g[0].device)
+            flat = self.flat_all[starts[bi]:starts[bi] + sizes[bi]]
             off = 0
             for p in g:
                 if p.dtype != torch.float32:
@@ -79,8 +87,7 @@ class GradAllReducer:
             for p in self.params:
                 p.grad = None
             return
-        for b in self.buckets:
-            b.zero_()
+        self.flat_all.zero_()
         self._pending = list(self._size)
         self._works = []
 
@@ -102,8 +109,16 @@ class GradAllReducer:
         (parameters unused in this step keep a zero gradient)."""
         if not self.enabled:
             return
+        op = self._avg if self._avg is not None else dist.ReduceOp.SUM
+        if not self.overlap:
+            dist.all_reduce(self.flat_all, op=op, group=self.group, async_op=True).wait()
+            if self._avg is None:
+                self.flat_all.div_(self.world)
+            self._pending = [0] * len(self._pending)
+            self._works = []
+            return
         for bi, left in enumerate(self._pending):
-            if left != 0 or not self.overlap:
+            if left != 0:
                 op = self._avg if self._avg is not None else dist.ReduceOp.SUM
                 self._works.append((dist.all_reduce(self.buckets[bi], op=op, group=self.group, async_op=True), bi))
                 self._pending[bi] = 0

@@ -33,7 +33,15 @@ def _worker(rank, world, port, q):
         red.zero_grad()
         torch.nn.functional.cross_entropy(m(xs), ys).backward()
         red.finish()
-    q.put((rank, [p.grad.clone() for p in m.parameters()]))
+    grads = [p.grad.clone() for p in m.parameters()]
+    # deferred mode (what a CUDA-graph replay of backward uses): hooks are silent, finish() reduces the one flat buffer
+    red.overlap = False
+    red.zero_grad()
+    torch.nn.functional.cross_entropy(m(xs), ys).backward()
+    red.finish()
+    for g, p in zip(grads, m.parameters()):
+        assert torch.allclose(g, p.grad, rtol=1e-6, atol=1e-7)
+    q.put((rank, grads))
     dist.barrier()
     dist.destroy_process_group()
 
