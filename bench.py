@@ -240,31 +240,42 @@ def graph_time_us(fn, iters, nbuf):
 
 
 def sppp_kernel_rooflines(wl, B, device, peaks):
-    """The three SPPP launches of a step, each timed alone through a CUDA graph of 16 launches over 8 rotating input
-    buffers (8 x 38.5 MB of embeddings: nothing survives in the 126 MB L2), against the measured copy bandwidth."""
+    """The three SPPP launches of a step, each timed alone through a CUDA graph of 16 launches over rotating input
+    buffers (8 x 38.5 MB of embeddings at the workload's batch: nothing survives in the 126 MB L2), against the measured
+    copy bandwidth.  At the workload's batch a launch moves 45-103 MB, i.e. 7-16 us at peak, so ~5 us of launch, ramp
+    and tail weigh in; `at_4x_batch` repeats the measurement at four times the batch (3 buffers), where they do not."""
     from favit_b200 import ops, synth
-    nbuf, iters = 8, 16
     S, ps, K, D = wl["img"], wl["ps"], wl["K"], wl["D"]
     P = (S // ps) ** 2
-    lms = [synth.voronoi_label_maps(B, S, K, seed=77 + i, device=device, exact_k=True, patch_size=ps) for i in range(nbuf)]
-    asg = [ops.sppp_assign(lm, ps, S, K) for lm in lms]
-    x = [torch.randn(B, P, D, device=device).to(torch.bfloat16) for _ in range(nbuf)]
-    g = [torch.randn(B, K, D, device=device) for _ in range(nbuf)]
-    out = {}
 
-    def rec(name, us, nbytes):
-        gbps = nbytes / us / 1e3
-        out[name] = {"us_per_launch": round(us, 2), "algorithmic_bytes": int(nbytes), "gbps": round(gbps, 1),
-                     "frac_hbm": round(gbps / peaks["hbm"], 4),
-                     "timing": "CUDA graph of 16 launches over 8 rotating buffers (L2-cold), CUDA events"}
+    def measure(Bm, nbuf, iters):
+        lms = [synth.voronoi_label_maps(Bm, S, K, seed=77 + i, device=device, exact_k=True, patch_size=ps)
+               for i in range(nbuf)]
+        asg = [ops.sppp_assign(lm, ps, S, K) for lm in lms]
+        x = [torch.randn(Bm, P, D, device=device).to(torch.bfloat16) for _ in range(nbuf)]
+        g = [torch.randn(Bm, K, D, device=device) for _ in range(nbuf)]
+        res = {}
 
-    rec("sppp_assign", graph_time_us(lambda i: ops.sppp_assign(lms[i], ps, S, K), iters, nbuf),
-        B * S * S * 8.0 + 2.0 * B * P * 4 + B * K * 4)
-    rec("sppp_pool_fwd", graph_time_us(lambda i: ops.sppp_pool_fwd(x[i], asg[i][6], asg[i][5], asg[i][2], K, torch.float32),
-                                       iters, nbuf),
-        B * P * D * 2.0 + B * P * 4 + B * K * D * 4.0 + B * K * 4)
-    rec("sppp_pool_bwd", graph_time_us(lambda i: ops.sppp_pool_bwd(g[i], asg[i][1], asg[i][3], torch.bfloat16), iters, nbuf),
-        B * K * D * 4.0 + B * P * 4 + B * P * D * 2.0)
+        def rec(name, us, nbytes):
+            gbps = nbytes / us / 1e3
+            res[name] = {"us_per_launch": round(us, 2), "algorithmic_bytes": int(nbytes), "gbps": round(gbps, 1),
+                         "frac_hbm": round(gbps / peaks["hbm"], 4)}
+
+        rec("sppp_assign", graph_time_us(lambda i: ops.sppp_assign(lms[i], ps, S, K), iters, nbuf),
+            Bm * S * S * 8.0 + 2.0 * Bm * P * 4 + Bm * K * 4)
+        rec("sppp_pool_fwd",
+            graph_time_us(lambda i: ops.sppp_pool_fwd(x[i], asg[i][6], asg[i][5], asg[i][2], K, torch.float32), iters, nbuf),
+            Bm * P * D * 2.0 + Bm * P * 4 + Bm * K * D * 4.0 + Bm * K * 4)
+        rec("sppp_pool_bwd",
+            graph_time_us(lambda i: ops.sppp_pool_bwd(g[i], asg[i][1], asg[i][3], torch.bfloat16), iters, nbuf),
+            Bm * K * D * 4.0 + Bm * P * 4 + Bm * P * D * 2.0)
+        return res
+
+    out = measure(B, 8, 16)
+    big = measure(4 * B, 3, 9)
+    for k, v in out.items():
+        v["timing"] = "CUDA graph of 16 launches over 8 rotating buffers (L2-cold), CUDA events"
+        v["at_4x_batch"] = {"batch": 4 * B, **{kk: big[k][kk] for kk in ("us_per_launch", "gbps", "frac_hbm")}}
     return out
 
 
