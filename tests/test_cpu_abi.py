@@ -66,3 +66,39 @@ def test_host_side_shapes_via_fake_tensors():
         assert y.shape == (34, 1152) and y.dtype == torch.bfloat16
         r = ops.sppp_assign(torch.empty(2, 224, 224, dtype=torch.int64, device="cuda"), 16, 224, 16)
         assert [t.shape for t in r] == [(2, 196), (2, 196), (2,), (2, 16), (2, 16), (2, 17), (2, 196)]
+        out, lse = ops.mhla_attn(qkv, 7, None, 0.1, 1234)          # attention-probability dropout arguments
+        assert out.shape == (2, 17, 384) and lse.shape == (2, 6, 17)
+        c = ops.sppp_centroids(torch.empty(2, 224, 224, dtype=torch.int64, device="cuda"), 16)
+        assert c.shape == (2, 16, 2) and c.dtype == torch.float32
+
+
+def test_dropout_keep_mask_is_a_fair_coin_and_seed_dependent():
+    """The oracle side of the counter-based dropout mask (the CUDA side is compared with it bit for bit on the GPU)."""
+    import numpy as np
+    import oracle
+    for p in (0.1, 0.5):
+        m = oracle.dropout_keep_mask(4, 6, 65, 7, p, seed=99)
+        assert m.shape == (4, 6, 65, 7) and abs(m.mean() - (1 - p)) < 0.02
+        assert abs(m[..., 0].mean() - m[..., 6].mean()) < 0.05        # no slot bias
+    a, b = oracle.dropout_keep_mask(1, 1, 50, 7, 0.5, 1), oracle.dropout_keep_mask(1, 1, 50, 7, 0.5, 2)
+    assert (a != b).mean() > 0.3
+    assert np.array_equal(a, oracle.dropout_keep_mask(1, 1, 50, 7, 0.5, 1))
+
+
+def test_oracle_gather_core_equals_closed_form():
+    """The two CPU formulations of the attention core (reference order of operations vs banded softmax with integer
+    multiplicities) agree, with and without a mask, for N < W, N = 1 and wide windows."""
+    import torch
+    import oracle
+    torch.manual_seed(1)
+    for (N, W) in [(10, 7), (3, 7), (1, 7), (40, 15), (17, 31), (6, 1)]:
+        q, k, v = [torch.randn(2, 2, N, 16, dtype=torch.float64) for _ in range(3)]
+        mask = (torch.rand(2, N, N) > 0.3).double()
+        mask[:, torch.arange(N), torch.arange(N)] = 1
+        # rows whose whole window is masked are NaN in both; keep the diagonal and the edge keys visible
+        mask[:, :, 0] = 1
+        mask[:, :, N - 1] = 1
+        for m in (None, mask):
+            a = oracle.mhla_attn_core_gather(q, k, v, W, m)
+            b, _ = oracle.mhla_attn_core_closed_form(q, k, v, W, m)
+            assert torch.allclose(a, b, rtol=1e-10, atol=1e-12), (N, W, m is None)
