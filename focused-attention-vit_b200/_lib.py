@@ -41,6 +41,10 @@ _SIGS = {
     "favit_sppp_assign": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "favit_sppp_centroids": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "favit_sppp_pool_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_pool_max_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_pool_max_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_pool_attn_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_sppp_pool_attn_bwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_bwd": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
 }
 

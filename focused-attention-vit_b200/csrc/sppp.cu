@@ -23,6 +23,7 @@
 // The older warp-per-item kernels remain as the fallback for shapes the tiled ones do not take (odd strides, huge R).
 #include <cuda.h>
 #include <limits.h>
+#include <math_constants.h>
 
 #include <algorithm>
 #include <mutex>
@@ -666,9 +667,9 @@ __global__ void __launch_bounds__(kPoolThreads) sppp_pool_fwd_tma_kernel(
   constexpr int NV = Group8<TIn>::N;
   constexpr int CW = kSliceBytes / (int)sizeof(TIn);
   // All shared memory is dynamic so that the TMA destination sits at the (128-byte aligned) base of the window.
-  extern __shared__ __align__(128) unsigned char s_raw[];
+  extern __shared__ __align__(128) unsigned char s_tile0[];
   const uint32_t tile_bytes = (uint32_t)P * kSliceBytes;
-  unsigned char* ring = s_raw;
+  unsigned char* ring = s_tile0;
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + (size_t)stages * tile_bytes);  // [4]
   int* s_order = reinterpret_cast<int*>(s_bar + 4);  // [2][P]
   int* s_off = s_order + 2 * P;                      // [2][R+1]
@@ -769,8 +770,8 @@ __global__ void __launch_bounds__(kSortedThreads) sppp_pool_fwd_sorted_kernel(
   constexpr int kCopyRows = kSortedThreads / PIECES;  // rows per copy pass
   constexpr uint32_t kChunkBytes = kChunkPos * SLICE;
   static_assert(kChunkBytes == kSortedChunkBytes, "stage size");
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  unsigned char* ring = s_raw;                                                         // [3][128][128 B]
+  extern __shared__ __align__(128) unsigned char s_tile1[];
+  unsigned char* ring = s_tile1;                                                         // [3][128][128 B]
   float* s_head = reinterpret_cast<float*>(ring + kSortedStages * kChunkBytes);        // [kLanes][CGS][NV]
   float* s_carry = s_head + kLanes * CGS * NV;                                              // [2][16][NV]
   int* s_cont = reinterpret_cast<int*>(s_carry + 2 * CGS * NV);                        // [kLanes] head goes on past its lane
@@ -985,6 +986,168 @@ __global__ void __launch_bounds__(kBwdThreads) sppp_pool_bwd_tile_kernel(const T
     } else {
       *reinterpret_cast<float4*>(o + (int64_t)p * D) = make_float4(f[0], f[1], f[2], f[3]);
     }
+  }
+}
+
+// =====================================================================================================
+// 'max' and 'attention' pooling (models/sppp.py:178-184 / 211-216): the non-default SuperpixelPooling variants.
+// One 128-thread CTA per (image, slot) walks the slot's CSR list in ascending patch order; threads own columns.
+// These are completeness kernels (no reference config selects them): coalesced and deterministic, not tuned.
+// =====================================================================================================
+constexpr int kVarThreads = 128;
+
+__device__ __forceinline__ float block_sum_128(float v, float* s_red) {  // every thread gets the sum; s_red [4]
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return s_red[0] + s_red[1] + s_red[2] + s_red[3];
+}
+
+// out[b,r,c] = max over the slot's patches of x[b,p,c]; argmax[b,r,c] = that patch (first one on ties), -1 if none.
+template <typename TIn>
+__global__ void __launch_bounds__(kVarThreads) sppp_pool_max_fwd_kernel(const TIn* __restrict__ x,
+                                                                        const int32_t* __restrict__ order,
+                                                                        const int32_t* __restrict__ offsets,
+                                                                        const int32_t* __restrict__ num_slots,
+                                                                        float* __restrict__ out,
+                                                                        int32_t* __restrict__ argmax, int P, int R, int D,
+                                                                        int r_cap) {
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  int beg = 0, end = 0;
+  if (r < r_cap && r < num_slots[b]) {
+    beg = offsets[(int64_t)b * (r_cap + 1) + r];
+    end = offsets[(int64_t)b * (r_cap + 1) + r + 1];
+  }
+  const int32_t* ord = order + (int64_t)b * P;
+  const TIn* xb = x + (int64_t)b * P * D;
+  for (int c = threadIdx.x; c < D; c += kVarThreads) {
+    float best = 0.f;
+    int arg = -1;
+    for (int t = beg; t < end; ++t) {
+      const int p = ord[t];
+      const float v = Elem<TIn>::ld(xb + (int64_t)p * D + c);
+      if (arg < 0 || v > best) {
+        best = v;
+        arg = p;
+      }
+    }
+    out[((int64_t)b * R + r) * D + c] = best;
+    argmax[((int64_t)b * R + r) * D + c] = arg;
+  }
+}
+
+// dx (zeroed by the caller) [b, argmax[b,r,c], c] = dout[b,r,c]; slots are disjoint, so no two threads meet
+template <typename TOut>
+__global__ void __launch_bounds__(256) sppp_pool_max_bwd_kernel(const float* __restrict__ dout,
+                                                                const int32_t* __restrict__ argmax,
+                                                                TOut* __restrict__ dx, int64_t total, int P, int R, int D) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = argmax[i];
+  if (p < 0) return;
+  const int c = (int)(i % D);
+  const int64_t b = i / ((int64_t)R * D);
+  Elem<TOut>::st(dx + (b * P + p) * D + c, dout[i]);
+}
+
+// weights[b,p] = softmax over the slot's patches of sum_c x[b,p,c]; out[b,r,:] = sum_p weights[b,p] x[b,p,:]
+template <typename TIn>
+__global__ void __launch_bounds__(kVarThreads) sppp_pool_attn_fwd_kernel(const TIn* __restrict__ x,
+                                                                         const int32_t* __restrict__ order,
+                                                                         const int32_t* __restrict__ offsets,
+                                                                         const int32_t* __restrict__ num_slots,
+                                                                         float* __restrict__ out,
+                                                                         float* __restrict__ weights, int P, int R, int D,
+                                                                         int r_cap) {
+  extern __shared__ float s_w[];  // [slot length] logits, then weights
+  __shared__ float s_red[4];
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int beg = 0, end = 0;
+  if (r < r_cap && r < num_slots[b]) {
+    beg = offsets[(int64_t)b * (r_cap + 1) + r];
+    end = offsets[(int64_t)b * (r_cap + 1) + r + 1];
+  }
+  const int n = end - beg;
+  const int32_t* ord = order + (int64_t)b * P + beg;
+  const TIn* xb = x + (int64_t)b * P * D;
+  // logits: one warp per patch, lane-strided partial sums, shuffle tree (fixed order)
+  for (int k = wid; k < n; k += kVarThreads / 32) {
+    const TIn* row = xb + (int64_t)ord[k] * D;
+    float sum = 0.f;
+    for (int c = lane; c < D; c += 32) sum += Elem<TIn>::ld(row + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_w[k] = sum;
+  }
+  __syncthreads();
+  float mx = -CUDART_INF_F;
+  for (int k = threadIdx.x; k < n; k += kVarThreads) mx = fmaxf(mx, s_w[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[wid] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  float part = 0.f;
+  for (int k = threadIdx.x; k < n; k += kVarThreads) {
+    const float e = expf(s_w[k] - mx);
+    s_w[k] = e;
+    part += e;
+  }
+  const float denom = block_sum_128(part, s_red);  // barriers inside: s_w is complete afterwards
+  const float inv = n > 0 ? 1.f / denom : 0.f;
+  for (int k = threadIdx.x; k < n; k += kVarThreads) {
+    const float w = s_w[k] * inv;
+    s_w[k] = w;
+    weights[(int64_t)b * P + ord[k]] = w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += kVarThreads) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc = fmaf(s_w[k], Elem<TIn>::ld(xb + (int64_t)ord[k] * D + c), acc);
+    out[((int64_t)b * R + r) * D + c] = acc;
+  }
+}
+
+// dx[p,c] = w_p dy[c] + w_p (dy . x_p - dy . y_r)   (dx zeroed by the caller for patches outside every kept slot)
+template <typename TIn>
+__global__ void __launch_bounds__(kVarThreads) sppp_pool_attn_bwd_kernel(const TIn* __restrict__ x,
+                                                                         const float* __restrict__ dout,
+                                                                         const float* __restrict__ out,
+                                                                         const float* __restrict__ weights,
+                                                                         const int32_t* __restrict__ order,
+                                                                         const int32_t* __restrict__ offsets,
+                                                                         const int32_t* __restrict__ num_slots,
+                                                                         TIn* __restrict__ dx, int P, int R, int D,
+                                                                         int r_cap) {
+  __shared__ float s_red[4];
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int beg = 0, end = 0;
+  if (r < r_cap && r < num_slots[b]) {
+    beg = offsets[(int64_t)b * (r_cap + 1) + r];
+    end = offsets[(int64_t)b * (r_cap + 1) + r + 1];
+  }
+  const int n = end - beg;
+  const int32_t* ord = order + (int64_t)b * P + beg;
+  const float* dy = dout + ((int64_t)b * R + r) * D;
+  const float* y = out + ((int64_t)b * R + r) * D;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < D; c += kVarThreads) part = fmaf(dy[c], y[c], part);
+  const float t_r = block_sum_128(part, s_red);
+  for (int k = wid; k < n; k += kVarThreads / 32) {
+    const int p = ord[k];
+    const TIn* row = x + ((int64_t)b * P + p) * D;
+    float dot = 0.f;
+    for (int c = lane; c < D; c += 32) dot = fmaf(dy[c], Elem<TIn>::ld(row + c), dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float w = weights[(int64_t)b * P + p];
+    const float dl = w * (dot - t_r);
+    TIn* drow = dx + ((int64_t)b * P + p) * D;
+    for (int c = lane; c < D; c += 32) Elem<TIn>::st(drow + c, fmaf(w, dy[c], dl));
   }
 }
 
@@ -1209,6 +1372,81 @@ extern "C" int favit_sppp_pool_fwd(const void* x, favit_dtype x_dtype, const int
     return launch_pool_fwd<float, __nv_bfloat16>(x, order, offsets, num_slots, out, B, P, R, D, r_cap, st);
   set_error("sppp_pool_fwd: bad dtype");
   return FAVIT_ERR_ARG;
+}
+
+extern "C" int favit_sppp_pool_max_fwd(const void* x, favit_dtype x_dtype, const int32_t* order, const int32_t* offsets,
+                                       const int32_t* num_slots, float* out, int32_t* argmax, int B, int P, int R, int D,
+                                       int r_cap, favit_stream stream) {
+  FAVIT_CHECK_ARG(x && order && offsets && num_slots && out && argmax, "sppp_pool_max_fwd: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && P > 0 && R > 0 && D > 0 && r_cap > 0 && (int64_t)B * R < INT_MAX, "sppp_pool_max_fwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == FAVIT_BF16)
+    sppp_pool_max_fwd_kernel<__nv_bfloat16><<<(unsigned)(B * R), kVarThreads, 0, st>>>((const __nv_bfloat16*)x, order, offsets,
+                                                                                    num_slots, out, argmax, P, R, D, r_cap);
+  else if (x_dtype == FAVIT_F32)
+    sppp_pool_max_fwd_kernel<float><<<(unsigned)(B * R), kVarThreads, 0, st>>>((const float*)x, order, offsets, num_slots, out,
+                                                                            argmax, P, R, D, r_cap);
+  else { set_error("sppp_pool_max_fwd: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+extern "C" int favit_sppp_pool_max_bwd(const float* dout, const int32_t* argmax, void* dx, favit_dtype dx_dtype, int B, int P,
+                                       int R, int D, favit_stream stream) {
+  FAVIT_CHECK_ARG(dout && argmax && dx, "sppp_pool_max_bwd: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && P > 0 && R > 0 && D > 0, "sppp_pool_max_bwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)B * R * D;
+  const size_t es = dx_dtype == FAVIT_BF16 ? 2 : 4;
+  FAVIT_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * P * D * es, st));
+  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  if (dx_dtype == FAVIT_BF16)
+    sppp_pool_max_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(dout, argmax, (__nv_bfloat16*)dx, total, P, R, D);
+  else if (dx_dtype == FAVIT_F32)
+    sppp_pool_max_bwd_kernel<float><<<blocks, 256, 0, st>>>(dout, argmax, (float*)dx, total, P, R, D);
+  else { set_error("sppp_pool_max_bwd: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+extern "C" int favit_sppp_pool_attn_fwd(const void* x, favit_dtype x_dtype, const int32_t* order, const int32_t* offsets,
+                                        const int32_t* num_slots, float* out, float* weights, int B, int P, int R, int D,
+                                        int r_cap, favit_stream stream) {
+  FAVIT_CHECK_ARG(x && order && offsets && num_slots && out && weights, "sppp_pool_attn_fwd: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && P > 0 && R > 0 && D > 0 && r_cap > 0 && (int64_t)B * R < INT_MAX, "sppp_pool_attn_fwd: bad sizes");
+  FAVIT_CHECK_ARG(P <= 12000, "sppp_pool_attn_fwd: more than 12000 patches per image unsupported");
+  cudaStream_t st = (cudaStream_t)stream;
+  FAVIT_CHECK_CUDA(cudaMemsetAsync(weights, 0, (size_t)B * P * sizeof(float), st));  // patches outside every kept slot
+  const size_t smem = (size_t)P * sizeof(float);
+  if (x_dtype == FAVIT_BF16)
+    sppp_pool_attn_fwd_kernel<__nv_bfloat16><<<(unsigned)(B * R), kVarThreads, smem, st>>>(
+        (const __nv_bfloat16*)x, order, offsets, num_slots, out, weights, P, R, D, r_cap);
+  else if (x_dtype == FAVIT_F32)
+    sppp_pool_attn_fwd_kernel<float><<<(unsigned)(B * R), kVarThreads, smem, st>>>((const float*)x, order, offsets, num_slots,
+                                                                                out, weights, P, R, D, r_cap);
+  else { set_error("sppp_pool_attn_fwd: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}
+
+extern "C" int favit_sppp_pool_attn_bwd(const void* x, favit_dtype x_dtype, const float* dout, const float* out,
+                                        const float* weights, const int32_t* order, const int32_t* offsets,
+                                        const int32_t* num_slots, void* dx, int B, int P, int R, int D, int r_cap,
+                                        favit_stream stream) {
+  FAVIT_CHECK_ARG(x && dout && out && weights && order && offsets && num_slots && dx, "sppp_pool_attn_bwd: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && P > 0 && R > 0 && D > 0 && r_cap > 0 && (int64_t)B * R < INT_MAX, "sppp_pool_attn_bwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = x_dtype == FAVIT_BF16 ? 2 : 4;
+  FAVIT_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * P * D * es, st));
+  if (x_dtype == FAVIT_BF16)
+    sppp_pool_attn_bwd_kernel<__nv_bfloat16><<<(unsigned)(B * R), kVarThreads, 0, st>>>(
+        (const __nv_bfloat16*)x, dout, out, weights, order, offsets, num_slots, (__nv_bfloat16*)dx, P, R, D, r_cap);
+  else if (x_dtype == FAVIT_F32)
+    sppp_pool_attn_bwd_kernel<float><<<(unsigned)(B * R), kVarThreads, 0, st>>>((const float*)x, dout, out, weights, order,
+                                                                             offsets, num_slots, (float*)dx, P, R, D, r_cap);
+  else { set_error("sppp_pool_attn_bwd: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
 }
 
 extern "C" int favit_sppp_pool_bwd(const void* dout, favit_dtype dout_dtype, const int32_t* slot,

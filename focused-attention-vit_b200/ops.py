@@ -417,3 +417,146 @@ def _pool_backward(ctx, dout):
 
 
 sppp_pool.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+# ---- 'max' and 'attention' pooling (models/sppp.py:178-184, 211-216) -----------------------------------------------
+@torch.library.custom_op("favit::sppp_pool_max_fwd", mutates_args=())
+def sppp_pool_max_fwd(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int) -> Tuple[Tensor, Tensor]:
+    """x [B,P,D] -> (out fp32 [B,R,D], argmax int32 [B,R,D])."""
+    _cuda(x, order, offsets, num_slots)
+    x = x.contiguous()
+    B, P, D = x.shape
+    r_cap = offsets.shape[1] - 1
+    out = torch.empty((B, R, D), dtype=torch.float32, device=x.device)
+    arg = torch.empty((B, R, D), dtype=torch.int32, device=x.device)
+    if out.numel():
+        rc = L.call("sppp_pool_max", 0.0, L.lib().favit_sppp_pool_max_fwd, _p(x), _dt(x), _p(order), _p(offsets), _p(num_slots),
+                    _p(out), _p(arg), B, P, R, D, r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_max_fwd")
+    return out, arg
+
+
+@sppp_pool_max_fwd.register_fake
+def _(x, order, offsets, num_slots, R):
+    B, P, D = x.shape
+    return x.new_empty((B, R, D), dtype=torch.float32), x.new_empty((B, R, D), dtype=torch.int32)
+
+
+@torch.library.custom_op("favit::sppp_pool_max_bwd", mutates_args=())
+def sppp_pool_max_bwd(dout: Tensor, argmax: Tensor, P: int, dx_dtype: torch.dtype) -> Tensor:
+    _cuda(dout, argmax)
+    dout = dout.contiguous().float()
+    B, R, D = dout.shape
+    dx = torch.empty((B, P, D), dtype=dx_dtype, device=dout.device)
+    if dx.numel():
+        rc = L.call("sppp_pool_max", 0.0, L.lib().favit_sppp_pool_max_bwd, _p(dout), _p(argmax), _p(dx), _DT[dx_dtype], B, P, R, D,
+                    _stream())
+        L.check(rc, "favit_sppp_pool_max_bwd")
+    return dx
+
+
+@sppp_pool_max_bwd.register_fake
+def _(dout, argmax, P, dx_dtype):
+    return dout.new_empty((dout.shape[0], P, dout.shape[2]), dtype=dx_dtype)
+
+
+@torch.library.custom_op("favit::sppp_pool_max", mutates_args=())
+def sppp_pool_max(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int) -> Tuple[Tensor, Tensor]:
+    """Differentiable batched segment max: x [B,P,D] -> (fp32 [B,R,D], argmax)."""
+    return sppp_pool_max_fwd(x, order, offsets, num_slots, R)
+
+
+@sppp_pool_max.register_fake
+def _(x, order, offsets, num_slots, R):
+    B, P, D = x.shape
+    return x.new_empty((B, R, D), dtype=torch.float32), x.new_empty((B, R, D), dtype=torch.int32)
+
+
+def _pool_max_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.P, ctx.x_dtype = inputs[0].shape[1], inputs[0].dtype
+    ctx.set_materialize_grads(False)
+
+
+def _pool_max_backward(ctx, dout, darg):
+    (arg,) = ctx.saved_tensors
+    if dout is None:
+        return None, None, None, None, None
+    return sppp_pool_max_bwd(dout, arg, ctx.P, ctx.x_dtype), None, None, None, None
+
+
+sppp_pool_max.register_autograd(_pool_max_backward, setup_context=_pool_max_setup)
+
+
+@torch.library.custom_op("favit::sppp_pool_attn_fwd", mutates_args=())
+def sppp_pool_attn_fwd(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int) -> Tuple[Tensor, Tensor]:
+    """x [B,P,D] -> (out fp32 [B,R,D], weights fp32 [B,P])."""
+    _cuda(x, order, offsets, num_slots)
+    x = x.contiguous()
+    B, P, D = x.shape
+    r_cap = offsets.shape[1] - 1
+    out = torch.empty((B, R, D), dtype=torch.float32, device=x.device)
+    w = torch.empty((B, P), dtype=torch.float32, device=x.device)
+    if out.numel():
+        rc = L.call("sppp_pool_attn", 0.0, L.lib().favit_sppp_pool_attn_fwd, _p(x), _dt(x), _p(order), _p(offsets), _p(num_slots),
+                    _p(out), _p(w), B, P, R, D, r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_attn_fwd")
+    return out, w
+
+
+@sppp_pool_attn_fwd.register_fake
+def _(x, order, offsets, num_slots, R):
+    B, P, D = x.shape
+    return x.new_empty((B, R, D), dtype=torch.float32), x.new_empty((B, P), dtype=torch.float32)
+
+
+@torch.library.custom_op("favit::sppp_pool_attn_bwd", mutates_args=())
+def sppp_pool_attn_bwd(x: Tensor, dout: Tensor, out: Tensor, weights: Tensor, order: Tensor, offsets: Tensor,
+                       num_slots: Tensor) -> Tensor:
+    _cuda(x, dout, out, weights, order, offsets, num_slots)
+    x = x.contiguous()
+    dout = dout.contiguous().float()
+    B, P, D = x.shape
+    R = out.shape[1]
+    r_cap = offsets.shape[1] - 1
+    dx = torch.empty_like(x)
+    if dx.numel():
+        rc = L.call("sppp_pool_attn", 0.0, L.lib().favit_sppp_pool_attn_bwd, _p(x), _dt(x), _p(dout), _p(out), _p(weights),
+                    _p(order), _p(offsets), _p(num_slots), _p(dx), B, P, R, D, r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_attn_bwd")
+    return dx
+
+
+@sppp_pool_attn_bwd.register_fake
+def _(x, dout, out, weights, order, offsets, num_slots):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("favit::sppp_pool_attn", mutates_args=())
+def sppp_pool_attn(x: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, R: int) -> Tuple[Tensor, Tensor]:
+    """Differentiable batched attention pooling: x [B,P,D] -> (fp32 [B,R,D], softmax weights [B,P])."""
+    return sppp_pool_attn_fwd(x, order, offsets, num_slots, R)
+
+
+@sppp_pool_attn.register_fake
+def _(x, order, offsets, num_slots, R):
+    B, P, D = x.shape
+    return x.new_empty((B, R, D), dtype=torch.float32), x.new_empty((B, P), dtype=torch.float32)
+
+
+def _pool_attn_setup(ctx, inputs, output):
+    x, order, offsets, num_slots, R = inputs
+    ctx.save_for_backward(x, output[0], output[1], order, offsets, num_slots)
+    ctx.set_materialize_grads(False)
+
+
+def _pool_attn_backward(ctx, dout, dw):
+    x, out, w, order, offsets, num_slots = ctx.saved_tensors
+    if dw is not None:
+        raise RuntimeError("sppp_pool_attn: gradients through the returned weights are not supported")
+    if dout is None:
+        return None, None, None, None, None
+    return sppp_pool_attn_bwd(x, dout, out, w, order, offsets, num_slots), None, None, None, None
+
+
+sppp_pool_attn.register_autograd(_pool_attn_backward, setup_context=_pool_attn_setup)

@@ -111,8 +111,8 @@ class SuperpixelPooling:
         """[B,P,D] -> fp32 [B,R,D] for the whole batch.  Like `torch.stack` at sppp_mhla.py:300 this needs every image
         to have exactly R = num_superpixels slots; with validate=True that is checked (one small D2H read) and a
         RuntimeError raised otherwise."""
-        if self.pooling_type != 'mean':
-            raise NotImplementedError(f"favit kernels implement pooling_type='mean' only (got {self.pooling_type!r})")
+        if self.pooling_type not in ('mean', 'max', 'attention'):
+            raise ValueError(f"Unknown pooling type: {self.pooling_type}")
         if validate:
             ns = assignment.num_slots
             lo, hi = int(ns.min()), int(ns.max())
@@ -120,14 +120,19 @@ class SuperpixelPooling:
                 raise RuntimeError(f"stack expects each tensor to be equal size: images have between {lo} and {hi} "
                                    f"superpixel slots, expected {num_superpixels} (reference sppp_mhla.py:300)")
         a = assignment
-        return ops.sppp_pool(patch_embeddings, a.slot, a.counts, a.order, a.offsets, a.num_slots, num_superpixels)
+        return self._pool_op(patch_embeddings, a, num_superpixels)
+
+    def _pool_op(self, x: torch.Tensor, a: SuperpixelAssignment, R: int) -> torch.Tensor:
+        if self.pooling_type == 'max':          # sppp.py:178-179 / 211-212
+            return ops.sppp_pool_max(x, a.order, a.offsets, a.num_slots, R)[0]
+        if self.pooling_type == 'attention':    # sppp.py:180-184 / 213-216
+            return ops.sppp_pool_attn(x, a.order, a.offsets, a.num_slots, R)[0]
+        return ops.sppp_pool(x, a.slot, a.counts, a.order, a.offsets, a.num_slots, R)
 
     def pool(self, patch_embeddings: torch.Tensor, superpixel_to_patches: Dict[int, List[int]]) -> torch.Tensor:
         """Reference signature: [N,D] (or [B,N,D] with one shared dict) + dict -> [R,D] (or [B,R,D]), fp32."""
         if self.pooling_type not in ('mean', 'max', 'attention'):
             raise ValueError(f"Unknown pooling type: {self.pooling_type}")
-        if self.pooling_type != 'mean':
-            raise NotImplementedError(f"favit kernels implement pooling_type='mean' only (got {self.pooling_type!r})")
         x = patch_embeddings
         batched = x.dim() == 3
         xb = x if batched else x.unsqueeze(0)
@@ -142,5 +147,5 @@ class SuperpixelPooling:
                                      ex(a.offsets), ex(a.order), a.r_cap)
         if R == 0:
             return torch.zeros((B, 0, D) if batched else (0, D), device=x.device)
-        out = ops.sppp_pool(xb, a.slot, a.counts, a.order, a.offsets, a.num_slots, R)
+        out = self._pool_op(xb, a, R)
         return out if batched else out[0]

@@ -218,6 +218,26 @@ int favit_sppp_pool_bwd(const void* dout, favit_dtype dout_dtype, const int32_t*
                         void* dx, favit_dtype dx_dtype, int B, int P, int R, int D, int r_cap,
                         favit_stream stream);
 
+/* The non-default SuperpixelPooling variants (models/sppp.py:178-184, 211-216), same CSR inputs as the mean pool.
+ * 'max'      : out[b,r,c] = max over the slot's patches; argmax int32 [B,R,D] (patch id, -1 for an empty row) is saved
+ *              for the backward, which routes dout[b,r,c] to dx[b,argmax,c] (dx is zeroed by the call).
+ * 'attention': weights fp32 [B,P] = softmax over the slot's patches of sum_c x[b,p,c] (0 for patches outside every
+ *              kept slot); out[b,r,:] = sum_p weights[b,p] x[b,p,:].  Backward (dx has x's dtype, zeroed by the call):
+ *              dx[p,:] = w_p dout_r + w_p (dout_r . x_p - dout_r . out_r).
+ * out / dout are fp32 (the reference's `torch.zeros` default dtype, sppp.py:198). */
+int favit_sppp_pool_max_fwd(const void* x, favit_dtype x_dtype, const int32_t* order, const int32_t* offsets,
+                            const int32_t* num_slots, float* out, int32_t* argmax, int B, int P, int R, int D,
+                            int r_cap, favit_stream stream);
+int favit_sppp_pool_max_bwd(const float* dout, const int32_t* argmax, void* dx, favit_dtype dx_dtype, int B, int P,
+                            int R, int D, favit_stream stream);
+int favit_sppp_pool_attn_fwd(const void* x, favit_dtype x_dtype, const int32_t* order, const int32_t* offsets,
+                             const int32_t* num_slots, float* out, float* weights, int B, int P, int R, int D,
+                             int r_cap, favit_stream stream);
+int favit_sppp_pool_attn_bwd(const void* x, favit_dtype x_dtype, const float* dout, const float* out,
+                             const float* weights, const int32_t* order, const int32_t* offsets,
+                             const int32_t* num_slots, void* dx, int B, int P, int R, int D, int r_cap,
+                             favit_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

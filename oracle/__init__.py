@@ -35,4 +35,5 @@ from .sppp_oracle import (  # noqa: F401
     assign_oracle,
     pool_mean_oracle,
     pool_mean_batched_oracle,
+    pool_variant_batched_oracle,
 )

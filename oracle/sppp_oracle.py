@@ -115,3 +115,27 @@ def pool_mean_batched_oracle(x: torch.Tensor, slot: np.ndarray, num_slots: int) 
         cnt = torch.bincount(s[b], minlength=num_slots).clamp_min(1).to(torch.float64)
         out[b] /= cnt[:, None]
     return out
+
+
+def pool_variant_batched_oracle(x: torch.Tensor, slot: np.ndarray, num_slots: int, pooling_type: str) -> torch.Tensor:
+    """'max' / 'attention' pooling (models/sppp.py:178-184, 211-216) for a batch, slot by slot in the reference's order of
+    operations (differentiable torch ops; pass an fp64 leaf to get reference gradients from autograd)."""
+    B, P, D = x.shape
+    rows = []
+    for b in range(B):
+        out = []
+        for r in range(num_slots):
+            idx = np.nonzero(np.asarray(slot[b]) == r)[0]
+            if len(idx) == 0:
+                out.append(torch.zeros(D, dtype=x.dtype))
+                continue
+            e = x[b, torch.from_numpy(idx)]
+            if pooling_type == "max":
+                out.append(torch.max(e, dim=0)[0])
+            elif pooling_type == "attention":
+                w = torch.softmax(torch.sum(e, dim=-1), dim=-1)
+                out.append(torch.sum(e * w.unsqueeze(-1), dim=0))
+            else:
+                raise ValueError(f"Unsupported pooling type: {pooling_type}")
+        rows.append(torch.stack(out))
+    return torch.stack(rows)

@@ -157,6 +157,38 @@ def test_unequal_slot_counts_raise():
         SuperpixelPooling("median").pool(x[0], {0: [0]})
 
 
+@pytest.mark.parametrize("kind", ["max", "attention"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B,S,ps,K,D", [(3, 32, 4, 4, 24), (2, 224, 16, 16, 384), (2, 128, 8, 16, 100)])
+def test_pool_variants_fwd_bwd_vs_oracle(B, S, ps, K, D, dtype, kind):
+    """SuperpixelPooling('max' / 'attention') (sppp.py:178-184, 211-216): forward and the gradient w.r.t. the patch
+    embeddings against the reference's slot-by-slot torch ops in fp64 (autograd)."""
+    from favit_b200.sppp import SuperpixelPooling
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(B, S, K, seed=13, device="cpu", exact_k=True, patch_size=ps)
+    a = _assign(lm.numpy(), ps, S, r_cap=K)
+    P = (S // ps) ** 2
+    torch.manual_seed(1)
+    x = (torch.randn(B, P, D) * (0.3 if kind == "attention" else 1.0)).to(dtype)   # row sums are softmax logits
+    g = torch.randn(B, K, D)
+    slot = a.slot.cpu().numpy()
+    x64 = x.double().requires_grad_(True)
+    ref = oracle.pool_variant_batched_oracle(x64, slot, K, kind)
+    (ref * g.double()).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = SuperpixelPooling(kind).pool_batch(xc, a, K)
+    assert out.dtype == torch.float32 and out.shape == (B, K, D)
+    assert rel_err(out, ref.detach()) < 1e-5   # inputs are identical: fp32 math only
+    out.backward(g.cuda())
+    assert xc.grad.dtype == dtype
+    assert rel_err(xc.grad, x64.grad) < (5e-6 if dtype == torch.float32 else 8e-3)
+    # reference signature: one image, dict from map_patches
+    from favit_b200.sppp import PatchToSuperpixelMapper
+    d = PatchToSuperpixelMapper(ps).map_patches(lm[0].cuda(), S)
+    one = SuperpixelPooling(kind).pool(x[0].cuda(), d)
+    assert torch.allclose(one, out[0].detach(), rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("B,H,W,K", [(3, 32, 32, 4), (2, 224, 224, 16), (2, 37, 53, 9), (1, 512, 512, 64), (2, 64, 48, 300)])
 def test_centroids_match_reference_loop(B, H, W, K):
     """favit::sppp_centroids against the reference's per-image / per-label loop (sppp_mhla.py:236-262) restated in fp64:
