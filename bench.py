@@ -370,8 +370,11 @@ def run_favit(args, wl, rank, world, local_rank):
         x, y, maps = batches[i % nb]
         return step(x, y, maps)
 
+    loss_first = None
     for i in range(max(args.warmup, 5 if args.cuda_graph else 0)):   # graph mode: 3 eager steps, capture, 1 replay
-        dev_step(i)
+        l = dev_step(i)
+        if loss_first is None:
+            loss_first = float(l)
     torch.cuda.synchronize(device)
 
     # ---- device-resident throughput (`value`) with per-launch event timing for the roofline ----
@@ -448,8 +451,13 @@ def run_favit(args, wl, rank, world, local_rank):
         return float(loss_host[0])
 
     feeder.i = 0
-    e2e_ms = timed_steps(e2e_step, args.steps, dist_on, device) / args.steps
+    e2e_losses = []
+    e2e_ms = timed_steps(lambda i: e2e_losses.append(e2e_step(i)), args.steps, dist_on, device) / args.steps
     e2e_value = world * B / (e2e_ms / 1e3)
+    # the step must be doing real training: every loss read back is finite and the optimizer has moved it
+    import math
+    if not (math.isfinite(loss_first) and all(math.isfinite(v) for v in e2e_losses)):
+        raise RuntimeError(f"non-finite loss in the benchmark: first {loss_first}, e2e {e2e_losses}")
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -464,6 +472,8 @@ def run_favit(args, wl, rank, world, local_rank):
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        "loss": {"first_step": round(loss_first, 4), "last_step": round(e2e_losses[-1], 4),
+                 "note": "random labels, two alternating batches: the loss falls as AdamW memorises them"},
         "roofline": roofline,
         "kernel_families": families,
     }
@@ -515,7 +525,7 @@ def main():
         args2.workload, args2.no_cpu_baseline, args2.steps = "sppp_vits_mhla_224", True, max(args.steps, 20)
         o2 = run_favit(args2, WORKLOADS[args2.workload], rank, world, local_rank)
         out["also"] = {args2.workload: {k: o2[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches",
-                                                           "config", "kernel_families")}}
+                                                           "loss", "config", "kernel_families")}}
         # BASELINE configs[4] (high-resolution SPPP + MHLA inference, the per-GPU share of the 8-GPU batch)
         out["also"]["sppp_vits_mhla_512_infer"] = run_infer(torch.device("cuda", local_rank), 20, 3)
     if rank == 0:

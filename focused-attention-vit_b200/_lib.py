@@ -22,6 +22,7 @@ _SIGS = {
     "favit_version": ([], _i),
     "favit_device_cc": ([], _i),
     "favit_last_error": ([], C.c_char_p),
+    "favit_last_kernel": ([], C.c_char_p),
     "favit_launch_count": ([], _u64),
     "favit_mhla_attn_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
     "favit_cast_bf16_batched": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp], _i),
@@ -61,6 +62,7 @@ def lib() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python focused-attention-vit_b200/build.py` "
                 "(there is no CPU or PyTorch fallback for the favit ops)")
+        import torch  # noqa: F401  (loads libcudart.so.12, which the library links dynamically)
         l = C.CDLL(LIB_PATH)
         for name, (args, res) in _SIGS.items():
             fn = getattr(l, name)       # AttributeError if the symbol is not exported
@@ -75,6 +77,11 @@ def check(rc: int, what: str) -> None:
         msg = lib().favit_last_error().decode(errors="replace")
         kind = {1: "bad argument", 2: "unsupported", 3: "CUDA error", 4: "workspace"}.get(rc, f"status {rc}")
         raise RuntimeError(f"{what}: {kind}: {msg}")
+
+
+def last_kernel() -> str:
+    """Name and variant of the kernel the last dispatching C call on this thread chose (tests assert on it)."""
+    return lib().favit_last_kernel().decode(errors="replace")
 
 
 def launch_count() -> int:

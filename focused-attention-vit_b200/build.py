@@ -60,8 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
     if (force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)):
-        # -cudart static: the library carries its own runtime; streams are driver handles and are shared with torch.
-        cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
+        # -cudart shared: only the runtime entry points the library calls are referenced (libcudart.so.12, the copy torch
+        # has already loaded); a static runtime would embed the name table of every runtime API in the shipped .so.
+        cmd = [NVCC, *ARCH, "-shared", "-cudart", "shared", "-o", LIB, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

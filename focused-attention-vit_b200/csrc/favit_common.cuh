@@ -13,6 +13,8 @@ namespace favit {
 // thread-local last-error message (favit_last_error)
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// which kernel variant the dispatching entry point chose (favit_last_kernel; tests assert on it)
+void note_kernel(const char* fmt, ...);
 
 #define FAVIT_CHECK_ARG(cond, ...)                    \
   do {                                                \

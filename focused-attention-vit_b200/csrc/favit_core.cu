@@ -9,6 +9,7 @@ namespace favit {
 
 namespace {
 thread_local char g_err[512] = "";
+thread_local char g_kernel[192] = "";
 std::atomic<uint64_t> g_launches{0};
 }  // namespace
 
@@ -16,6 +17,13 @@ void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
   va_end(ap);
 }
 
@@ -38,6 +46,8 @@ int num_sms() {
 extern "C" int favit_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char* favit_last_error(void) { return favit::g_err; }
+
+extern "C" const char* favit_last_kernel(void) { return favit::g_kernel; }
 
 extern "C" uint64_t favit_launch_count(void) { return favit::g_launches.load(std::memory_order_relaxed); }
 

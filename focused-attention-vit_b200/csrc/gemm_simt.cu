@@ -112,6 +112,7 @@ int gemm_simt_launch(const float* A, const float* B, float* C, const float* bias
     splits = ceil_div(K, kps);
   }
   dim3 grid(ceil_div(N, TN), ceil_div(M, TM), splits > 1 ? splits : 1);
+  note_kernel("gemm_simt_kernel splits=%d", splits);
   gemm_simt_kernel<<<grid, 256, 0, st>>>(a);
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;

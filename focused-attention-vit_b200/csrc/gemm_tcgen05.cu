@@ -560,7 +560,10 @@ int gemm_bf16(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int
   // force_bn: 0 = auto (CTA-pair kernel for large shapes), 512 = CTA-pair kernel, 64/128/256 = this kernel
   if ((force_bn == 0 || force_bn == 512) && gemm_bf16_2cta_applicable(M, N, K, epi, lda, ldb))
     return gemm_bf16_2cta(A, a_mn, lda, B, b_mn, ldb, M, N, K, epi, force_splits, st);
-  if (force_bn == 512) force_bn = 0;
+  if (force_bn == 512) {  // the caller asked for the CTA-pair kernel by name: never substitute another one silently
+    set_error("gemm_tcgen05: the CTA-pair kernel does not apply to M=%d N=%d K=%d with this epilogue", M, N, K);
+    return FAVIT_ERR_UNSUPPORTED;
+  }
   const int sms = num_sms();
   const int m_tiles = ceil_div(M, BM);
   const int k_blocks = ceil_div(K, BK);
@@ -617,6 +620,7 @@ int gemm_bf16(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int
   kp.epi = epi;
   const int64_t units = tiles * splits;
   const int grid = (int)min((int64_t)sms, units);
+  note_kernel("gemm_bf16_tcgen05_kernel<BN=%d> act=%d splits=%d a_mn=%d b_mn=%d", bn, epi.act, splits, a_mn, b_mn);
   switch (bn) {
     case 64: return launch<64>(ta, tb, kp, grid, st);
     case 128: return launch<128>(ta, tb, kp, grid, st);

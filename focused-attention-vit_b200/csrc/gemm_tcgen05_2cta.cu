@@ -511,6 +511,8 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.reduce = (splits > 1 || epi.accumulate) ? 1 : 0;
   kp.colsum = epi.colsum;
   const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
+  note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d", aux ? 1 : 0,
+              kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn);
   return aux ? launch<true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
              : launch<false>(ta, tb, tcm, tc2, taux, kp, clusters, st);
 }

@@ -416,11 +416,16 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
   FAVIT_CHECK_ARG(out && lse, "mhla_attn_fwd: null out/lse");
   const bool drop = dropout_p > 0.f;  // dropout (training, non-default) runs on the general kernels
   if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
-      ((uintptr_t)out % 16) == 0)
+      ((uintptr_t)out % 16) == 0) {
+    note_kernel("attn_seq_fwd (TMA whole-sequence, mma.sync)");
     return attn_seq_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
-  if (!drop && attn_mma_applicable(hd, window, dtype, mask))
+  }
+  if (!drop && attn_mma_applicable(hd, window, dtype, mask)) {
+    note_kernel("attn_mma_fwd (per-warp staging, mma.sync)");
     return attn_mma_fwd(q, k, v, out, lse, B, H, N, hd, window, scale, stride_b, stride_n, stride_h,
                         (cudaStream_t)stream);
+  }
+  note_kernel("attn_simt_fwd");
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
   if (drop) { sh.drop_p = dropout_p; sh.inv_keep = 1.f / (1.f - dropout_p); sh.seed = seed; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -445,12 +450,17 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
   const bool drop = dropout_p > 0.f;
   if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
       ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
-      ((uintptr_t)dv % 16) == 0)
+      ((uintptr_t)dv % 16) == 0) {
+    note_kernel("attn_seq_bwd (TMA whole-sequence, mma.sync)");
     return attn_seq_bwd(q, k, v, out, lse, dout, dq, dk, dv, dqkv_colsum, B, H, N, window, scale, stride_b, stride_n,
                         stride_h, (cudaStream_t)stream);
-  if (!drop && attn_mma_applicable(hd, window, dtype, mask))
+  }
+  if (!drop && attn_mma_applicable(hd, window, dtype, mask)) {
+    note_kernel("attn_mma_bwd (per-warp staging, mma.sync)");
     return attn_mma_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, dqkv_colsum, B, H, N, hd, window, scale, stride_b,
                         stride_n, stride_h, (cudaStream_t)stream);
+  }
+  note_kernel("attn_simt_bwd");
   AttnShape sh{B, H, N, window, stride_b, stride_n, stride_h, scale * kLog2e, scale};
   if (drop) { sh.drop_p = dropout_p; sh.inv_keep = 1.f / (1.f - dropout_p); sh.seed = seed; }
   cudaStream_t st = (cudaStream_t)stream;

@@ -1189,6 +1189,7 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
       int per_sm = (int)((220 * 1024) / (smem + 1024));
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
       const int grid = nitems < num_sms() * per_sm ? nitems : num_sms() * per_sm;
+      note_kernel("sppp_pool_fwd_tma_kernel grid=%d items=%d stages=%d", grid, nitems, stages);
       sppp_pool_fwd_tma_kernel<TIn, TOut><<<grid, kPoolThreads, smem, st>>>(
           tm, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, nslices, nitems, stages);
       FAVIT_CHECK_LAUNCH();
@@ -1214,6 +1215,7 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
       const int sl_items = B * ceil_div(D * (int)sizeof(TIn), slice);
       const int grid = sl_items < num_sms() * per_sm ? sl_items : num_sms() * per_sm;
+      note_kernel("sppp_pool_fwd_sorted_kernel<%d> grid=%d items=%d", slice, grid, sl_items);
       if (narrow)
         sppp_pool_fwd_sorted_kernel<TIn, TOut, 64><<<grid, kSortedThreads, smem, st>>>(
             (const TIn*)x, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, sl_items / B, sl_items);
@@ -1228,6 +1230,7 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
   const int per = vec ? 256 : 32;
   const int64_t items = (int64_t)B * R * ceil_div(D, per);
   const unsigned blocks = (unsigned)ceil_div64(items, 8);
+  note_kernel("sppp_pool_fwd_kernel<vec=%d>", vec ? 8 : 1);
   if (vec)
     sppp_pool_fwd_kernel<TIn, TOut, 8><<<blocks, 256, 0, st>>>((const TIn*)x, order, offsets, num_slots,
                                                                 (TOut*)out, B, P, R, D, r_cap);
@@ -1251,6 +1254,7 @@ int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
+    note_kernel("sppp_pool_bwd_tile_kernel grid=%d", B * nslices);
     sppp_pool_bwd_tile_kernel<TIn, TOut><<<(unsigned)(B * nslices), kBwdThreads, smem, st>>>(
         (const TIn*)dout, slot, counts, (TOut*)dx, P, R, D, r_cap, nslices);
     FAVIT_CHECK_LAUNCH();
@@ -1260,6 +1264,7 @@ int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts
   const int per = vec ? 256 : 32;
   const int64_t items = (int64_t)B * P * ceil_div(D, per);
   const unsigned blocks = (unsigned)ceil_div64(items, 8);
+  note_kernel("sppp_pool_bwd_kernel<vec=%d>", vec ? 8 : 1);
   if (vec)
     sppp_pool_bwd_kernel<TIn, TOut, 8><<<blocks, 256, 0, st>>>((const TIn*)dout, slot, counts, (TOut*)dx, B, P,
                                                                 R, D, r_cap);

@@ -45,6 +45,10 @@ int favit_version(void);
 /* compute capability of the current device, major*10+minor (100 on B200); < 0 on error */
 int favit_device_cc(void);
 const char* favit_last_error(void);
+/* Thread-local description of the kernel variant the last dispatching entry point chose on this thread, e.g.
+ * "gemm_bf16_tcgen05_2cta_kernel<AUX=0> act=1 ..." or "sppp_pool_fwd_tma_kernel grid=592 ...": lets a test assert that
+ * the code path it means to check is the one that ran. */
+const char* favit_last_kernel(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t favit_launch_count(void);
 
