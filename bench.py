@@ -357,7 +357,7 @@ def run_favit(args, wl, rank, world, local_rank):
     model = build_model(wl, device)
     if wl["kind"] == "sppp":
         model.validate_slots = False          # synthetic maps are validated once, below, not once per step
-    step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph)
+    step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph, dp_mode=args.dp_mode)
     # distinct batches so that no step can reuse a cached input; seed differs per rank
     nb = 2
     batches = [make_batch(wl, B, seed=1234 + rank * 100 + i, device=device) for i in range(nb)]
@@ -377,61 +377,28 @@ def run_favit(args, wl, rank, world, local_rank):
             loss_first = float(l)
     torch.cuda.synchronize(device)
 
-    # ---- device-resident throughput (`value`) with per-launch event timing for the roofline ----
+    # ---- device-resident throughput (`value`) ----
     sampler = ClockSampler(local_rank)
-    L.PROFILE = None if args.cuda_graph else []   # per-launch events cannot be recorded inside a replayed graph
+    L.PROFILE = None if args.cuda_graph else []   # eager mode: per-launch events straight in the timed region
     launches0 = L.launch_count()
     sampler.start()
     ms_total = timed_steps(dev_step, args.steps, dist_on, device)
     clocks = sampler.stop()
     launches = L.launch_count() - launches0
     prof, L.PROFILE = (L.PROFILE or []), None
-    if args.cuda_graph:
-        # launch count and per-family timing come from one eager step of the same model (outside the timed region)
-        L.PROFILE = []
-        l0 = L.launch_count()
-        step._eager(*batches[0])
-        torch.cuda.synchronize(device)
-        launches = (L.launch_count() - l0) * args.steps
-        prof, L.PROFILE = L.PROFILE, None
-        prof = prof * args.steps
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
+    fam_acc = {}            # (family, role) -> [work, ms, launches] over the profiled steps
 
-    fam = {}
-    for name, work, e0, e1 in prof:
-        f = fam.setdefault(name, [0.0, 0.0, 0])
-        f[0] += work
-        f[1] += e0.elapsed_time(e1)
-        f[2] += 1
-    peaks = load_peaks()
-    gemm = [fam[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in fam]
-    g_work, g_ms, g_n = (sum(v[0] for v in gemm), sum(v[1] for v in gemm), sum(v[2] for v in gemm)) if gemm else (0, 1, 0)
-    achieved = g_work / (g_ms * 1e-3) / 1e12
-    roofline = {
-        "kernel": "gemm_bf16_tcgen05_2cta_kernel / gemm_bf16_tcgen05_kernel: every GEMM launch of the timed region "
-                  "(MHLA qkv / proj and the block's fc1 / fc2; forward, dgrad, wgrad)",
-        "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-        "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None, "peak_source": peaks["source"] + " (sustained)",
-        "launches": g_n, "share_of_step": round(g_ms / ms_total, 4),
-    }
-    families = {k: {"launches": v[2], "ms_per_step": round(v[1] / args.steps, 4),
-                    ("gbps" if k.startswith(("sppp", "attn")) else "tflops"):
-                        round(v[0] / (v[1] * 1e-3) / (1e9 if k.startswith(("sppp", "attn")) else 1e12), 2)}
-                for k, v in fam.items() if v[1] > 0}
-    for k, v in families.items():
-        if "gbps" in v:
-            v["frac_hbm"] = round(v["gbps"] / peaks["hbm"], 4)
-    if wl["kind"] == "sppp" and rank == 0:
-        # ~10-20 us kernels: an eager event bracket measures launch latency, so these three are re-timed in a graph
-        for k, v in sppp_kernel_rooflines(wl, B, device, peaks).items():
-            v["launches"] = families.get(k, {}).get("launches", args.steps)
-            families[k] = v
-    tr = load_traffic(args.workload)
-    if tr:
-        roofline["traffic"] = tr["dram_bytes_per_launch"]
-        roofline["traffic_source"] = tr["source"]
-        roofline["algorithmic_bytes_per_launch"] = tr.get("algorithmic_bytes_per_launch")
+    def add(rec_list):
+        for name, role, work, e0, e1 in rec_list:
+            f = fam_acc.setdefault((name, role), [0.0, 0.0, 0])
+            f[0] += work
+            f[1] += e0.elapsed_time(e1)
+            f[2] += 1
+
+    add(prof)
+    prof_ms_step, prof_mode = ms_step, "events around every favit launch of the timed region (eager launches)"
 
     # ---- end to end from pinned host memory (`e2e`) ----
     host = [tuple(None if t is None else t.cpu().pin_memory() for t in b) for b in batches]
@@ -459,6 +426,87 @@ def run_favit(args, wl, rank, world, local_rank):
     if not (math.isfinite(loss_first) and all(math.isfinite(v) for v in e2e_losses)):
         raise RuntimeError(f"non-finite loss in the benchmark: first {loss_first}, e2e {e2e_losses}")
 
+    # ---- per-kernel timing inside REPLAYED steps: the step is captured once more with an external event node before
+    # and after every favit launch; after each replay the events hold that launch's duration inside the running step ----
+    if args.cuda_graph:
+        L.PROFILE = []
+        step.recapture()
+        l0 = L.launch_count()
+        dev_step(0)                                   # capture (one step's launches are recorded) + first replay
+        per_step_launches = L.launch_count() - l0
+        recs, L.PROFILE = L.PROFILE, None
+        launches = per_step_launches * args.steps
+        torch.cuda.synchronize(device)
+        tot = 0.0
+        for i in range(args.steps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            dev_step(i)
+            s1.record()
+            torch.cuda.synchronize(device)
+            tot += s0.elapsed_time(s1)
+            add(recs)
+        prof_ms_step = tot / args.steps
+        prof_mode = (f"external CUDA event nodes around every favit launch inside the captured step graph, read after each of "
+                     f"{args.steps} replays (instrumented step {prof_ms_step:.3f} ms vs {ms_step:.3f} ms uninstrumented)")
+    prof_total_ms = prof_ms_step * args.steps
+
+    fam = {}
+    for (name, role), v in fam_acc.items():
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        for j in range(3):
+            f[j] += v[j]
+    peaks = load_peaks()
+    gemm = [fam[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in fam]
+    g_work, g_ms, g_n = (sum(v[0] for v in gemm), sum(v[1] for v in gemm), sum(v[2] for v in gemm)) if gemm else (0, 1, 0)
+    achieved = g_work / (g_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "gemm_bf16_tcgen05_2cta_kernel (+ gemm_bf16_tcgen05_kernel for fc2-with-residual): every GEMM launch of "
+                  "the profiled steps (MHLA qkv / proj and the block's fc1 / fc2; forward, dgrad, wgrad)",
+        "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+        "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+        "launches": g_n, "avg_us_per_launch": round(g_ms * 1e3 / max(g_n, 1), 2), "share_of_step": round(g_ms / prof_total_ms, 4),
+        "timing": prof_mode,
+    }
+    # the metric's "MHLA kernel % of roofline": the MHLA module alone (mhla.py:85-161 and its autograd) = qkv GEMMs +
+    # window attention + proj GEMMs + latent fold, algorithmic FLOPs F_min = B N (8 D^2 + 4 W D) per layer forward
+    # (the latent projection is folded away), x3 for forward + backward
+    n_tok = (wl["img"] // wl["ps"]) ** 2 + 1 if wl["kind"] == "vit" else wl["K"] + 1
+    f_min = 3.0 * wl["depth"] * B * n_tok * (8.0 * wl["D"] ** 2 + 4.0 * wl["W"] * wl["D"]) * args.steps
+    parts = {}
+    for (name, role), v in fam_acc.items():
+        key = role if role in ("qkv", "attn", "proj") else ("fold" if name == "fold" else None)
+        if key:
+            parts[key] = parts.get(key, 0.0) + v[1]
+    mhla_ms = sum(parts.values())
+    roofline_mhla = None
+    if mhla_ms > 0:
+        a_m = f_min / (mhla_ms * 1e-3) / 1e12
+        roofline_mhla = {
+            "kernel": "MHLA module: qkv GEMM + window attention + proj GEMM + latent fold, forward and backward",
+            "bound": "tensor", "achieved": round(a_m, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+            "frac": round(a_m / peaks["tf_sust"], 4), "algorithmic_flops_per_step": f_min / args.steps,
+            "ms_per_step": {k: round(v / args.steps, 4) for k, v in parts.items()},
+            "share_of_step": round(mhla_ms / prof_total_ms, 4)}
+    families = {k: {"launches": v[2], "ms_per_step": round(v[1] / args.steps, 4),
+                    ("gbps" if k.startswith(("sppp", "attn", "ln")) else "tflops"):
+                        round(v[0] / (v[1] * 1e-3) / (1e9 if k.startswith(("sppp", "attn", "ln")) else 1e12), 2)}
+                for k, v in fam.items() if v[1] > 0}
+    for k, v in families.items():
+        if "gbps" in v:
+            v["frac_hbm"] = round(v["gbps"] / peaks["hbm"], 4)
+    if wl["kind"] == "sppp" and rank == 0:
+        # the three 10-20 us SPPP kernels are also timed alone, L2-cold, in a graph over rotating buffers
+        for k, v in sppp_kernel_rooflines(wl, B, device, peaks).items():
+            v["launches"] = families.get(k, {}).get("launches", args.steps)
+            v["in_step_us_per_launch"] = round(families[k]["ms_per_step"] * 1e3 * args.steps / max(families[k]["launches"], 1), 2) if k in families else None
+            families[k] = v
+    tr = load_traffic(args.workload)
+    if tr:
+        roofline["traffic"] = tr["dram_bytes_per_launch"]
+        roofline["traffic_source"] = tr["source"]
+        roofline["algorithmic_bytes_per_launch"] = tr.get("algorithmic_bytes_per_launch")
+
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
@@ -466,6 +514,10 @@ def run_favit(args, wl, rank, world, local_rank):
         "config": {"workload": args.workload, "global_batch": world * B, "per_gpu_batch": B, "img": wl["img"],
                    "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"], "window": wl["W"],
                    "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "adamw(fused) in step", "cuda_graph": bool(args.cuda_graph),
+                   "dp_mode": (args.dp_mode + (" (NCCL all-reduce nodes inside the step graph)" if args.cuda_graph and
+                                               args.dp_mode != "split" else "")) if dist_on else None,
+                   "grad_allreduce_calls_per_step": (len(step.reducer.buckets) if args.dp_mode == "overlap" else 1)
+                   if dist_on else 0,
                    "l2": "working set >> L2 every step (inputs %.0f MB, activations several GB); no flush needed"
                          % (h2d / 1e6)},
         "clocks": clocks,
@@ -475,6 +527,7 @@ def run_favit(args, wl, rank, world, local_rank):
         "loss": {"first_step": round(loss_first, 4), "last_step": round(e2e_losses[-1], 4),
                  "note": "random labels, two alternating batches: the loss falls as AdamW memorises them"},
         "roofline": roofline,
+        "roofline_mhla": roofline_mhla,
         "kernel_families": families,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -502,6 +555,9 @@ def main():
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true",
                     help="capture the training step in a CUDA graph (default)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split"],
+                    help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
+                         "(default), one collective after backward, or one collective outside the step graph")
     ap.set_defaults(cuda_graph=None)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "favit":

@@ -90,9 +90,13 @@ def launch_count() -> int:
 
 # ------------------------------------------------------------------------------------------------
 # optional per-launch timing (bench.py's roofline): when `PROFILE` is a list, every C call is bracketed by CUDA
-# events on the current torch stream and (family, algorithmic work, start, end) is appended to it.
+# events on the current torch stream and (family, role, algorithmic work, start, end) is appended to it.  While the
+# stream is being captured the events are recorded as EXTERNAL event nodes of the graph, so that after every replay
+# `start.elapsed_time(end)` is the duration of that launch inside the replayed step.
+# `ROLE` names the layer a launch belongs to (set by fused_block: "qkv", "attn", "proj", "fc1", "fc2", "ln", "fold").
 # ------------------------------------------------------------------------------------------------
 PROFILE = None
+ROLE = ""
 
 
 def call(family: str, work: float, fn, *args) -> int:
@@ -100,10 +104,11 @@ def call(family: str, work: float, fn, *args) -> int:
     if PROFILE is None:
         return fn(*args)
     import torch
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
+    ext = torch.cuda.is_current_stream_capturing()
+    e0 = torch.cuda.Event(enable_timing=True, external=ext)
+    e1 = torch.cuda.Event(enable_timing=True, external=ext)
     e0.record()
     rc = fn(*args)
     e1.record()
-    PROFILE.append((family, work, e0, e1))
+    PROFILE.append((family, ROLE, work, e0, e1))
     return rc

@@ -17,16 +17,24 @@ from .dp import GradAllReducer
 
 class TrainStep:
     """cuda_graph=True captures the whole step (forward, loss, backward with the overlapped all-reduce, AdamW) into one
-    CUDA graph after three eager warm-up steps and replays it afterwards: the launch-bound small workloads (SPPP +
+    CUDA graph after three eager warm-up steps (which also set up NCCL's communicator) and replays it afterwards: the launch-bound small workloads (SPPP +
     ViT-S: ~1300 launches of 5-10 us each) then run at GPU speed instead of Python speed.  Inputs are copied into the
     graph's static buffers; shapes must not change between calls."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.05,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 32.0,
-                 optimizer: bool = True, cuda_graph: bool = False):
+                 optimizer: bool = True, cuda_graph: bool = False, dp_mode: str = "overlap"):
+        """dp_mode (data parallel only): "overlap" = one coalesced all-reduce per gradient bucket, launched from the
+        backward hooks and running beside the rest of backward (also inside the captured graph); "deferred" = one
+        coalesced all-reduce of every gradient after backward (inside the graph when cuda_graph); "split" = deferred, with
+        the collective issued eagerly between two graphs (backward | AdamW), for NCCL builds that cannot be captured."""
+        if dp_mode not in ("overlap", "deferred", "split"):
+            raise ValueError(f"unknown dp_mode {dp_mode!r}")
+        self.dp_mode = dp_mode
         self.model = model
         self.autocast_dtype = autocast_dtype
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group)
+        self.reducer.overlap = dp_mode == "overlap"
         # lr / weight decay: the reference's defaults (main.py:129-132)
         self.opt = (torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
                                       capturable=cuda_graph)
@@ -55,23 +63,29 @@ class TrainStep:
         return loss
 
     def _capture(self, images, labels, segmentation_maps):
-        """Single GPU: one graph for the whole step.  Data parallel: graph A = zero_grad + forward + backward, then the
-        bucketed all-reduce is issued eagerly (NCCL collectives are kept out of stream capture), then graph B = AdamW.
-        The un-overlapped all-reduce costs ~1 ms of a ~37 ms ViT-B step at 8 GPUs; the eager path (cuda_graph=False)
-        keeps the overlap instead."""
+        """One graph for the whole step: zero_grad, forward, loss, backward, the gradient all-reduce(s) — forked onto
+        NCCL's stream by the backward hooks and joined before the optimizer — and AdamW.  dp_mode "split" keeps the
+        collective out of the capture: graph A = forward + backward, eager all-reduce, graph B = AdamW."""
         self._static = [images.clone(), labels.clone(), None if segmentation_maps is None else segmentation_maps.clone()]
         self._graph = torch.cuda.CUDAGraph()
-        if not self.reducer.enabled:
-            with torch.cuda.graph(self._graph):
+        if not (self.reducer.enabled and self.dp_mode == "split"):
+            # thread_local: NCCL's watchdog thread may query events while this thread captures
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                 self._static_loss = self._eager(*self._static)
             return
-        self.reducer.overlap = False
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             self._static_loss = self._fwd_bwd(*self._static)
         if self.opt is not None:
             self._graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
                 self.opt.step()
+
+    def recapture(self) -> None:
+        """Drop the captured graph(s); the next call captures the step again (bench.py re-captures with external event
+        nodes around every favit launch to time the kernels inside replayed steps)."""
+        self._graph = self._graph_opt = None
+        self._static = self._static_loss = None
+        self._calls = max(self._calls, 3)
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor,
                  segmentation_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -88,8 +102,8 @@ class TrainStep:
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
-        if self.reducer.enabled:
-            self.reducer.finish()                 # every bucket: hooks are off in deferred mode
+        if self.reducer.enabled and self.dp_mode == "split":
+            self.reducer.finish()                 # one coalesced all-reduce of the gradients the graph left in place
             if self._graph_opt is not None:
                 self._graph_opt.replay()
         return self._static_loss

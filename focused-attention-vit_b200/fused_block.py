@@ -16,16 +16,13 @@ matmuls whose autograd yields the latent_proj gradients).
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional
 
 import torch
 from torch import Tensor
 
+from . import _lib as L
 from . import raw
-
-# bf16 copy of the residual-stream gradient produced by a block's backward, handed to the next block's backward
-# (autograd only carries the fp32 gradient).  Keyed by the fp32 tensor's storage address; consumed once.
-_GRAD_BF16 = {}
 
 
 @torch.library.custom_op("favit::block_fwd", mutates_args=())
@@ -37,16 +34,23 @@ def block_fwd(x: Tensor, ln1_w: Tensor, ln1_b: Tensor, wqkv: Tensor, bqkv: Tenso
     M, D = x.shape
     cd = wqkv.dtype
     hd = D // H
-    _GRAD_BF16.clear()      # entries of an earlier backward pass must never be matched by a recycled address
+    L.ROLE = "ln"
     xn, mu1, rs1 = raw.ln_fwd(x, ln1_w, ln1_b, cd, eps1)
+    L.ROLE = "qkv"
     qkv, _ = raw.linear_fwd(xn, wqkv, bqkv, None, cd)
+    L.ROLE = "attn"
     o, lse = raw.attn_fwd(qkv, B, N, H, hd, window)
+    L.ROLE = "proj"
     # the attention branch joins the fp32 residual stream inside the LayerNorm kernel (coalesced row accesses) rather
     # than in the GEMM epilogue (one thread per row): same bytes, moved to where they stream at HBM speed
     a, _ = raw.linear_fwd(o, wproj, bproj, None, cd)
+    L.ROLE = "ln"
     xn2, mu2, rs2, x2 = raw.ln_fwd(x, ln2_w, ln2_b, cd, eps2, delta=a)
+    L.ROLE = "fc1"
     h, hpre = raw.linear_fwd(xn2, w1, b1, None, cd, gelu=True, save_preact=True)
+    L.ROLE = "fc2"
     x3, _ = raw.linear_fwd(h, w2, b2, x2, torch.float32)
+    L.ROLE = ""
     return [x3, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h]
 
 
@@ -65,51 +69,58 @@ def _(x, ln1_w, ln1_b, wqkv, bqkv, wproj, bproj, ln2_w, ln2_b, w1, b1, w2, b2, B
 @torch.library.custom_op("favit::block_bwd", mutates_args=())
 def block_bwd(g: Tensor, x: Tensor, ln1_w: Tensor, wqkv: Tensor, wproj: Tensor, ln2_w: Tensor, w1: Tensor, w2: Tensor,
               xn: Tensor, mu1: Tensor, rs1: Tensor, qkv: Tensor, o: Tensor, lse: Tensor, x2: Tensor, xn2: Tensor,
-              mu2: Tensor, rs2: Tensor, hpre: Tensor, h: Tensor, B: int, N: int, H: int, window: int) -> List[Tensor]:
-    """Returns [dx, small, dwqkv, dwproj, dw1, dw2, db2] (all fp32); `small` packs every small gradient of the block in
-    one buffer (custom-op outputs may not alias each other): see `unpack_block_grads`."""
+              mu2: Tensor, rs2: Tensor, hpre: Tensor, h: Tensor, B: int, N: int, H: int, window: int,
+              g_c: Optional[Tensor] = None, gsum: Optional[Tensor] = None) -> List[Tensor]:
+    """Returns [dx, small, dwqkv, dwproj, dw1, dw2, db2, dx_c] (fp32 except dx_c); `small` packs every small gradient of
+    the block in one buffer (custom-op outputs may not alias each other): see `unpack_block_grads`.  `dx_c` is dx in
+    the compute dtype (empty in fp32 mode) and the last D entries of `small` are its column sums: the LayerNorm
+    backward produces both on the way, and the caller may hand them to the block below as `g_c` / `gsum` (the operand
+    copy and column sums of THAT block's incoming gradient g, i.e. its fc2 bias gradient) — explicitly, and only when
+    it knows that g is the very tensor they were derived from (see FusedBlockPrefoldedFn.backward)."""
     M, D = x.shape
     cd = wqkv.dtype
     hd = D // H
     bf = cd == torch.bfloat16
     g = g.contiguous()
-    # (operand copy in the compute dtype, column sums) of the incoming gradient, left behind by the LayerNorm backward of
-    # the block above; the column sums are this block's fc2 bias gradient
-    handed = _GRAD_BF16.pop((g.data_ptr(), M, D), None)
-    if handed is not None:
-        g_c, gsum = handed
-    else:
+    if g_c is None:
         g_c, gsum = (g.to(cd) if bf else g), None
     # every small accumulator of this backward (bias-gradient column sums, LayerNorm dgamma / dbeta) lives in one zeroed
     # buffer: one fill launch per block instead of four
     Hd = w2.shape[1]
     z = torch.zeros((Hd + 9 * D,), dtype=torch.float32, device=x.device)
     z_db1, z_ln2, z_attn, z_ln1 = z[:Hd], z[Hd:Hd + 3 * D].view(3, D), z[Hd + 3 * D:Hd + 6 * D], z[Hd + 6 * D:].view(3, D)
+    L.ROLE = "fc2"
     dw2, db2 = raw.linear_wgrad(g_c, h, want_bias=gsum is None)
     if gsum is not None:
         db2 = gsum
     dhpre, db1 = raw.linear_dgrad(g_c, w2, hpre, cd, colsum=True, zeroed=z_db1)   # fc1's bias gradient (GELU' epilogue)
+    L.ROLE = "fc1"
     dw1, _ = raw.linear_wgrad(dhpre, xn2, want_bias=False)
     dxn2 = raw.linear_dgrad(dhpre, w1, None, cd)
+    L.ROLE = "ln"
     g2, g2_b, dg2, dbt2, dbp = raw.ln_bwd(dxn2, x2, mu2, rs2, ln2_w, g, bf, zeroed=z_ln2)   # dbp = column sums of g2
     g2_c = g2_b if bf else g2
+    L.ROLE = "proj"
     dwp, _ = raw.linear_wgrad(g2_c, o, want_bias=False)
     do = raw.linear_dgrad(g2_c, wproj, None, cd)
+    L.ROLE = "attn"
     dqkv, dbq = raw.attn_bwd(qkv, o, lse, do, B, N, H, hd, window, zeroed=z_attn)   # qkv bias gradient on the way
+    L.ROLE = "qkv"
     dwq, _ = raw.linear_wgrad(dqkv, xn, want_bias=False)
     dxn = raw.linear_dgrad(dqkv, wqkv, None, cd)
+    L.ROLE = "ln"
     g0, g0_b, dg1, dbt1, g0sum = raw.ln_bwd(dxn, x, mu1, rs1, ln1_w, g2, bf, zeroed=z_ln1)
-    _GRAD_BF16.clear()                          # at most one hand-over is alive
-    _GRAD_BF16[(g0.data_ptr(), M, D)] = (g0_b if bf else g0, g0sum)
+    L.ROLE = ""
     # db2 is either the wgrad's own output or the column sums handed over by the block above (a slice of THAT block's
     # buffer): a private copy keeps this op's outputs free of aliases
-    return [g0, z, dwq, dwp, dw1, dw2, db2.clone() if gsum is not None else db2]
+    return [g0, z, dwq, dwp, dw1, dw2, db2.clone() if gsum is not None else db2,
+            g0_b if bf else g0.new_empty((0,), dtype=cd)]
 
 
 def unpack_block_grads(outs, D: int, Hd: int):
     """block_bwd outputs -> (dx, dln1_w, dln1_b, dwqkv, dbqkv, dwproj, dbproj, dln2_w, dln2_b, dw1, db1, dw2, db2).
     Layout of `small`: [db1 (Hd) | dln2_w, dln2_b, dbproj (3 x D) | dbqkv (3D) | dln1_w, dln1_b, column sums of dx (3 x D)]."""
-    g0, z, dwq, dwp, dw1, dw2, db2 = outs
+    g0, z, dwq, dwp, dw1, dw2, db2 = outs[:7]
     db1 = z[:Hd]
     ln2 = z[Hd:Hd + 3 * D].view(3, D)
     dbq = z[Hd + 3 * D:Hd + 6 * D]
@@ -118,12 +129,15 @@ def unpack_block_grads(outs, D: int, Hd: int):
 
 
 @block_bwd.register_fake
-def _(g, x, ln1_w, wqkv, wproj, ln2_w, w1, w2, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h, B, N, H, window):
+def _(g, x, ln1_w, wqkv, wproj, ln2_w, w1, w2, xn, mu1, rs1, qkv, o, lse, x2, xn2, mu2, rs2, hpre, h, B, N, H, window,
+      g_c=None, gsum=None):
     f32 = torch.float32
     e = lambda t: t.new_empty(t.shape, dtype=f32)
     D = x.shape[1]
     v = lambda n: x.new_empty((n,), dtype=f32)
-    return [e(x), v(w2.shape[1] + 9 * D), e(wqkv), e(wproj), e(w1), e(w2), v(D)]
+    cd = wqkv.dtype
+    dxc = x.new_empty(x.shape if cd == torch.bfloat16 else (0,), dtype=cd)
+    return [e(x), v(w2.shape[1] + 9 * D), e(wqkv), e(wproj), e(w1), e(w2), v(D), dxc]
 
 
 @torch.library.custom_op("favit::latent_fold_fwd", mutates_args=())
@@ -261,8 +275,24 @@ class FusedBlockPrefoldedFn(torch.autograd.Function):
         if g2d.dtype != torch.float32:
             g2d = g2d.float()
         f = lambda t: t.detach().float().contiguous()
-        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = unpack_block_grads(block_bwd(
-            g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window), D, w2_c.shape[1])
+        # Hand-over from the block above (layer + 1), whose backward ran just before this one in the chain run_blocks
+        # built: the compute-dtype copy of its dx and the column sums of dx, both by-products of its LayerNorm backward.
+        # They are used only if the gradient autograd delivers here IS that dx, unmodified: same storage (the entry
+        # keeps dx alive, so the address cannot have been recycled) and same version counter (autograd accumulates
+        # fan-out gradients in place, which bumps it).  Anything else (a module between the blocks, a second consumer
+        # of the block's input) falls back to casting g.
+        g_c = gsum = None
+        handed = ctx.stash.pop(("handover", ctx.layer + 1), None)
+        if handed is not None:
+            dx_above, ver, dx_c, dxsum = handed
+            if (g2d.data_ptr() == dx_above.data_ptr() and g2d.shape == dx_above.shape and g2d.is_contiguous()
+                    and g2d._version == ver and dx_above._version == ver):
+                g_c, gsum = (dx_c if dx_c.numel() else g2d), dxsum
+        outs = block_bwd(g2d, x2d, f(ln1_w), wq_c, wp_c, f(ln2_w), w1_c, w2_c, *saved, B, N, H, window, g_c, gsum)
+        (dx, dln1_w, dln1_b, dwq, dbq, dwp, dbp, dln2_w, dln2_b, dw1, db1, dw2, db2) = unpack_block_grads(
+            outs, D, w2_c.shape[1])
+        if ctx.layer > 0:
+            ctx.stash[("handover", ctx.layer)] = (dx, dx._version, outs[7], outs[1][-D:])
         ctx.stash[ctx.layer] = (dwq, dbq, dwp, dbp)
         gtok = torch.zeros(1, dtype=torch.float32, device=dx.device) if ctx.has_token else None
         return (dx.view(B, N, D), gtok, dln1_w, dln1_b, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None, None,

@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
     red.finish()
     for g, p in zip(grads, m.parameters()):
         assert torch.allclose(g, p.grad, rtol=1e-6, atol=1e-7)
-    q.put((rank, grads))
+    q.put((rank, [g.numpy() for g in grads]))      # by value: the worker may exit before the parent reads
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,7 +66,7 @@ def test_two_rank_gloo_matches_single_process_large_batch():
     torch.nn.functional.cross_entropy(m(x), y).backward()
     for r in range(2):
         for g, p in zip(res[r], m.parameters()):
-            assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(torch.from_numpy(g), p.grad, rtol=1e-5, atol=1e-6)
 
 
 def test_single_process_is_a_noop_reducer():

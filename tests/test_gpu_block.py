@@ -123,3 +123,84 @@ def test_batched_latent_fold_matches_per_layer_fold():
         assert torch.allclose(dl[i][0], dlw, rtol=1e-5, atol=1e-4) and torch.allclose(dl[i][1], dlb, rtol=1e-5, atol=1e-4)
         for g, r in zip(grads[i][:3], ref_in[i][:3]):    # rewritten in place by both
             assert torch.equal(g, r)
+
+
+def _stack_case(mid, towers):
+    """Blocks run through models.run_blocks (batched fold + the explicit bf16-gradient hand-over between consecutive
+    blocks) in arrangements where the gradient that reaches a block is NOT the tensor the block above produced."""
+    from favit_b200.models import TransformerBlock, run_blocks
+    torch.manual_seed(11)
+    B, N, D, H, W = 2, 17, 128, 2, 7
+    mk = lambda: torch.nn.ModuleList([TransformerBlock(embed_dim=D, num_heads=H, window_size=W, use_mhla=True)
+                                      for _ in range(2)]).cuda()
+    stacks = [mk() for _ in range(towers)]
+    tail = mk()
+    x = torch.randn(B, N, D)
+    g = torch.randn(B, N, D)
+
+    def forward(xin, blocks_fn, scale):
+        outs = [blocks_fn(s, xin) for s in stacks]
+        y = outs[0] if towers == 1 else outs[0] + outs[1]
+        if mid:                                  # two element-wise ops between the fused stacks
+            y = y * scale + 0.25
+        return blocks_fn(tail, y)
+
+    xc = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = forward(xc, lambda s, t: run_blocks(s, t), 1.5)
+    y.backward(g.cuda())
+    xr = x.double().requires_grad_(True)
+
+    def oracle_stack(s, t):
+        sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in s.state_dict().items()}
+        oracle_stack.sds.append((s, sd))
+        for i in range(len(s)):
+            t = oracle_block(t, sd, f"{i}.", H, W)
+        return t
+    oracle_stack.sds = []
+    yr = forward(xr, oracle_stack, 1.5)
+    yr.backward(g.double())
+    assert_close(y, yr, torch.bfloat16, "stack y")
+    assert_close(xc.grad, xr.grad, torch.bfloat16, "stack dx", factor=2.0)
+    for s, sd in oracle_stack.sds:
+        for k, p in s.named_parameters():
+            assert_close(p.grad, sd[k].grad, torch.bfloat16, f"stack d{k}", factor=3.0,
+                         floor=1e-3 * float(xr.grad.abs().max()))
+
+
+@pytest.mark.parametrize("mid,towers", [(False, 1), (True, 1), (False, 2), (True, 2)],
+                         ids=["chain", "ops_between", "two_towers", "two_towers_ops_between"])
+def test_block_gradient_handover_is_tied_to_the_tensor(mid, towers):
+    _stack_case(mid, towers)
+
+
+def test_second_backward_without_forward_reuses_nothing_stale():
+    """backward(retain_graph=True) twice with different output gradients: the second pass must not pick up the
+    operand copy / column sums the first pass left behind."""
+    from favit_b200.models import TransformerBlock, run_blocks
+    torch.manual_seed(12)
+    B, N, D, H, W = 2, 17, 128, 2, 7
+    blocks = torch.nn.ModuleList([TransformerBlock(embed_dim=D, num_heads=H, window_size=W, use_mhla=True)
+                                  for _ in range(3)]).cuda()
+    x = torch.randn(B, N, D, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = run_blocks(blocks, x)
+    g1, g2 = torch.randn_like(y), torch.randn_like(y)
+    y.backward(g1, retain_graph=True)
+    first = {k: p.grad.clone() for k, p in blocks.named_parameters()}
+    dx1 = x.grad.clone()
+    for p in blocks.parameters():
+        p.grad = None
+    x.grad = None
+    y.backward(g2, retain_graph=True)
+    second = {k: p.grad.clone() for k, p in blocks.named_parameters()}
+    dx2 = x.grad.clone()
+    # linearity of backward in the output gradient: a third pass with g1 + g2 equals the sum of the two
+    for p in blocks.parameters():
+        p.grad = None
+    x.grad = None
+    y.backward(g1 + g2)
+    assert_close(x.grad, dx1 + dx2, torch.bfloat16, "dx linearity")
+    scale = float(max(v.abs().max() for v in first.values()))
+    for k, p in blocks.named_parameters():
+        assert_close(p.grad, first[k] + second[k], torch.bfloat16, f"linearity d{k}", floor=1e-2 * scale)
