@@ -10,6 +10,9 @@ the bucketed gradient all-reduce overlapped -> AdamW step, on a fixed per-GPU ba
 Workloads:
   vitb16_mhla_224    VisionTransformerMHLA ViT-B/16, 224px, window 7, per-GPU batch 256       (BASELINE configs[3]; default)
   sppp_vits_mhla_224 SPPPViTMHLA ViT-S/16, 224px, 16 superpixels, window 7, per-GPU batch 256  (BASELINE configs[1])
+  vit_tiny_cifar_32  VisionTransformerMHLA tiny, 32px / patch 4, D 192, dropout 0.1, batch 64  (BASELINE configs[0])
+The default run also reports, under "also": configs[1], configs[0], configs[4] (512 px SPPP inference, every rank runs its
+32-image share of the 256-image batch, no communication) and configs[2] (the attention / SPPP microbenchmark sweeps).
 
 `--impl reference` times the CPU restatement of the reference (oracle/, the reference itself is Python and does not
 travel to the GPU box) on the host cores, on a bounded sample of the same workload.
@@ -32,6 +35,10 @@ WORKLOADS = {
     "vitb16_mhla_224": dict(kind="vit", img=224, ps=16, D=768, depth=12, H=12, W=7, classes=1000, B=256, cpu_B=8),
     "sppp_vits_mhla_224": dict(kind="sppp", img=224, ps=16, D=384, depth=12, H=6, W=7, K=16, classes=1000, B=256,
                                cpu_B=16),
+    # BASELINE configs[0]: the reference's own CPU-runnable case, main.py-style (dropout 0.1 in the MLP, main.py:106;
+    # batch 64, main.py:90; AdamW lr 1e-4 wd 0.05, main.py:129-132); the CPU arm runs it at the full batch
+    "vit_tiny_cifar_32": dict(kind="vit", img=32, ps=4, D=192, depth=12, H=3, W=7, classes=10, B=64, cpu_B=64,
+                              dropout=0.1),
 }
 METRIC = "images/sec fwd+bwd ViT-MHLA 224px"
 
@@ -51,11 +58,12 @@ def build_model(wl, device):
     torch.manual_seed(1234)
     if wl["kind"] == "vit":
         m = VisionTransformerMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
-                                  depth=wl["depth"], num_heads=wl["H"], window_size=wl["W"], use_mhla=True)
+                                  depth=wl["depth"], num_heads=wl["H"], window_size=wl["W"], use_mhla=True,
+                                  dropout=wl.get("dropout", 0.0))
     else:
         m = SPPPViTMHLA(img_size=wl["img"], patch_size=wl["ps"], num_classes=wl["classes"], embed_dim=wl["D"],
                         depth=wl["depth"], num_heads=wl["H"], num_superpixels=wl["K"], window_size=wl["W"],
-                        use_mhla=True, pooling_type="mean")
+                        use_mhla=True, pooling_type="mean", dropout=wl.get("dropout", 0.0))
     return m.to(device)
 
 
@@ -145,7 +153,7 @@ def cpu_oracle_step_fn(wl, B):
     def step():
         opt.zero_grad(set_to_none=True)
         if wl["kind"] == "vit":
-            logits = oracle.vit_mhla_forward(x, sd, wl["ps"], wl["H"], wl["W"])
+            logits = oracle.vit_mhla_forward(x, sd, wl["ps"], wl["H"], wl["W"], mlp_dropout=wl.get("dropout", 0.0))
         else:
             logits = oracle.sppp_vit_mhla_forward(x, maps, sd, wl["ps"], wl["H"], wl["W"], wl["K"])
         loss = torch.nn.functional.cross_entropy(logits, y)
@@ -279,6 +287,70 @@ def sppp_kernel_rooflines(wl, B, device, peaks):
     return out
 
 
+def attn_sweep(device, peaks, iters=8):
+    """BASELINE configs[2], attention part: favit_mhla_attn_fwd / bwd over sequence lengths 17..4097 (latent tokens
+    16-256 + cls, patch tokens 64-4096 + cls), 3 and 12 heads of 64, windows 7 (reference default) / 15 / 31 / 63, bf16,
+    B*N ~ 64k tokens; each kernel in a CUDA graph of `iters` launches over 3 rotating inputs.  Algorithmic bytes:
+    forward 4 B N D e, backward 8 B N D e; `frac` is of the measured copy bandwidth."""
+    from favit_b200 import _lib as L, raw
+    bf = torch.bfloat16
+    rows = []
+    for N in (17, 65, 197, 257, 1025, 4097):
+        for H in (3, 12):
+            for W in (7, 15, 31, 63):
+                hd = 64
+                D = H * hd
+                B = max(1, 65536 // N)
+                M = B * N
+                qkv = [torch.randn(M, 3 * D, device=device).to(bf) for _ in range(3)]
+                do = [torch.randn(M, D, device=device).to(bf) for _ in range(3)]
+                fwd = graph_time_us(lambda i: raw.attn_fwd(qkv[i], B, N, H, hd, W), iters, 3)
+                kern = L.last_kernel().split(" ")[0]
+                o, lse = raw.attn_fwd(qkv[0], B, N, H, hd, W)
+                bwd = graph_time_us(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, hd, W)[0], iters, 3)
+                fb, bb = 4.0 * M * D * 2, 8.0 * M * D * 2
+                rows.append({"N": N, "H": H, "W": W, "B": B, "kernel": kern, "fwd_us": round(fwd, 1),
+                             "fwd_frac_hbm": round(fb / fwd / 1e3 / peaks["hbm"], 3), "bwd_us": round(bwd, 1),
+                             "bwd_frac_hbm": round(bb / bwd / 1e3 / peaks["hbm"], 3),
+                             "gflops_fwd": round(4.0 * M * W * D / fwd / 1e3, 1)})
+                del qkv, do, o, lse
+    return {"what": "MHLA window-attention microbenchmark (BASELINE configs[2]); bf16, head_dim 64, B*N ~ 64k tokens",
+            "timing": f"CUDA graph of {iters} launches over 3 rotating inputs, best of 5 replays, CUDA events",
+            "rows": rows}
+
+
+def sppp_sweep(device, peaks, iters=8):
+    """BASELINE configs[2], SPPP part: favit_sppp_assign / pool_fwd / pool_bwd over patch tokens P in {64..4096},
+    superpixel (latent) tokens R in {16, 64, 256}, D in {192, 384, 768}, bf16 embeddings, B*P ~ 50k patches."""
+    from favit_b200 import ops, synth
+    shapes = {64: (32, 4), 196: (224, 16), 256: (128, 8), 1024: (256, 8), 4096: (512, 8)}
+    rows = []
+    for P, (S, ps) in shapes.items():
+        for R in (16, 64, 256):
+            if R * 4 > P:
+                continue            # fewer than 4 patches per superpixel: not a configuration the models can reach
+            B = max(2, 50176 // P)
+            lms = [synth.voronoi_label_maps(B, S, R, seed=5 + i, device=device, patch_size=ps) for i in range(3)]
+            asg = [ops.sppp_assign(lm, ps, S, R) for lm in lms]
+            t_as = graph_time_us(lambda i: ops.sppp_assign(lms[i], ps, S, R), iters, 3)
+            for D in (192, 384, 768):
+                x = [torch.randn(B, P, D, device=device).to(torch.bfloat16) for _ in range(3)]
+                g = [torch.randn(B, R, D, device=device) for _ in range(3)]
+                tf = graph_time_us(lambda i: ops.sppp_pool_fwd(x[i], asg[i][6], asg[i][5], asg[i][2], R, torch.float32), iters, 3)
+                tb = graph_time_us(lambda i: ops.sppp_pool_bwd(g[i], asg[i][1], asg[i][3], torch.bfloat16), iters, 3)
+                bf_ = B * P * D * 2.0 + B * P * 4 + B * R * D * 4.0 + B * R * 4
+                bb_ = B * R * D * 4.0 + B * P * 4 + B * P * D * 2.0
+                ba_ = B * S * S * 8.0 + 2.0 * B * P * 4 + B * R * 4
+                rows.append({"P": P, "R": R, "D": D, "B": B, "assign_us": round(t_as, 1),
+                             "assign_frac_hbm": round(ba_ / t_as / 1e3 / peaks["hbm"], 3), "pool_fwd_us": round(tf, 1),
+                             "pool_fwd_frac_hbm": round(bf_ / tf / 1e3 / peaks["hbm"], 3), "pool_bwd_us": round(tb, 1),
+                             "pool_bwd_frac_hbm": round(bb_ / tb / 1e3 / peaks["hbm"], 3)})
+                del x, g
+    return {"what": "SPPP microbenchmark (BASELINE configs[2]): patch tokens x superpixel tokens x width",
+            "timing": f"CUDA graph of {iters} launches over 3 rotating inputs, best of 5 replays, CUDA events",
+            "rows": rows}
+
+
 def load_traffic(workload):
     """Per-launch DRAM bytes of the roofline kernel from the committed ncu capture (profiles/r1_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -288,10 +360,11 @@ def load_traffic(workload):
         return None
 
 
-def run_infer(device, steps, warmup):
+def run_infer(device, steps, warmup, rank=0, world=1, dist_on=False):
     """BASELINE configs[4]: high-resolution SPPP + MHLA inference (512 px, patch 8 -> 4096 patch tokens pooled to 64
-    superpixel tokens), 32 images per GPU (the per-GPU share of a batch of 256 on 8 GPUs; no communication).  Forward
-    only, eval mode, bf16 autocast, captured in a CUDA graph; inputs resident in HBM, two alternating batches."""
+    superpixel tokens), 32 images per GPU: the batch of 256 sharded over 8 GPUs, no communication (every rank runs its
+    own images; with fewer ranks the global batch is world x 32).  Forward only, eval mode, bf16 autocast, captured in a
+    CUDA graph; inputs resident in HBM, two alternating batches; time = max over ranks."""
     from favit_b200 import synth
     from favit_b200.models import SPPPViTMHLA
     cfg = dict(img=512, ps=8, D=384, depth=12, H=6, K=64, W=7, B=32)
@@ -302,9 +375,9 @@ def run_infer(device, steps, warmup):
     m.validate_slots = False
     batches = []
     for i in range(2):
-        x = synth.images(cfg["B"], cfg["img"], seed=4321 + i, device=device)
-        maps = synth.voronoi_label_maps(cfg["B"], cfg["img"], cfg["K"], seed=4321 + i, device=device, exact_k=True,
-                                        patch_size=cfg["ps"])
+        x = synth.images(cfg["B"], cfg["img"], seed=4321 + i + 10 * rank, device=device)
+        maps = synth.voronoi_label_maps(cfg["B"], cfg["img"], cfg["K"], seed=4321 + i + 10 * rank, device=device,
+                                        exact_k=True, patch_size=cfg["ps"])
         batches.append((x, maps))
 
     def fwd(x, maps):
@@ -328,16 +401,17 @@ def run_infer(device, steps, warmup):
 
     for i in range(max(warmup, 3)):
         step(i)
-    ms = timed_steps(step, steps, False, device) / steps
-    return {"value": round(cfg["B"] / (ms / 1e3), 1), "unit": "images/s, forward only (eval, no_grad)",
-            "ms_per_step": round(ms, 3), "steps": steps,
-            "config": {"workload": "sppp_vits_mhla_512_infer", "per_gpu_batch": cfg["B"], "img": cfg["img"],
+    ms = timed_steps(step, steps, dist_on, device) / steps
+    return {"value": round(world * cfg["B"] / (ms / 1e3), 1), "unit": "images/s, forward only (eval, no_grad)",
+            "ms_per_step": round(ms, 3), "steps": steps, "n_gpus": world, "scaling": "weak (batch sharded, no collective)",
+            "config": {"workload": "sppp_vits_mhla_512_infer", "global_batch": world * cfg["B"],
+                       "per_gpu_batch": cfg["B"], "img": cfg["img"],
                        "patch": cfg["ps"], "patch_tokens": (cfg["img"] // cfg["ps"]) ** 2, "superpixels": cfg["K"],
                        "embed_dim": cfg["D"], "depth": cfg["depth"], "heads": cfg["H"], "window": cfg["W"],
                        "cuda_graph": True, "dtype": "bf16"}}
 
 
-def run_favit(args, wl, rank, world, local_rank):
+def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl=favit) needs a B200: the favit kernels have no CPU fallback")
@@ -535,7 +609,7 @@ def run_favit(args, wl, rank, world, local_rank):
         out["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
                                "sample": f"{wl['cpu_B']} images/step of {args.workload} (fp32 oracle port, 1 warm-up + 2 "
                                          f"timed steps, AdamW included)"}
-    if dist_on:
+    if dist_on and not keep_pg:
         dist.barrier()
         dist.destroy_process_group()
     return out
@@ -574,16 +648,32 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run "
                          f"--nproc-per-node {args.gpus}")
-    out = run_favit(args, wl, rank, world, local_rank)
-    if world == 1 and args.also and args.workload == "vitb16_mhla_224":
-        # BASELINE configs[1] (SPPP + MHLA ViT-S, batch 256) measured in the same run, reported under "also"
-        args2 = argparse.Namespace(**vars(args))
-        args2.workload, args2.no_cpu_baseline, args2.steps = "sppp_vits_mhla_224", True, max(args.steps, 20)
-        o2 = run_favit(args2, WORKLOADS[args2.workload], rank, world, local_rank)
-        out["also"] = {args2.workload: {k: o2[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches",
-                                                           "loss", "config", "kernel_families")}}
-        # BASELINE configs[4] (high-resolution SPPP + MHLA inference, the per-GPU share of the 8-GPU batch)
-        out["also"]["sppp_vits_mhla_512_infer"] = run_infer(torch.device("cuda", local_rank), 20, 3)
+    also_on = args.also and args.workload == "vitb16_mhla_224"
+    out = run_favit(args, wl, rank, world, local_rank, keep_pg=also_on)
+    if also_on:
+        device = torch.device("cuda", local_rank)
+        also = {}
+        if world == 1:
+            keys = ("value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches", "loss", "config", "roofline_mhla",
+                    "kernel_families")
+            # BASELINE configs[1] (SPPP + MHLA ViT-S, batch 256) and configs[0] (tiny CIFAR-shaped ViT + MHLA, batch 64,
+            # dropout 0.1) measured in the same run
+            for name, steps2, cpu in (("sppp_vits_mhla_224", max(args.steps, 20), False),
+                                      ("vit_tiny_cifar_32", max(args.steps, 20), True)):
+                args2 = argparse.Namespace(**vars(args))
+                args2.workload, args2.no_cpu_baseline, args2.steps = name, not cpu, steps2
+                o2 = run_favit(args2, WORKLOADS[name], rank, world, local_rank)
+                also[name] = {k: o2[k] for k in keys + (("cpu_baseline",) if cpu and "cpu_baseline" in o2 else ())}
+            peaks = load_peaks()
+            also["attn_sweep"] = attn_sweep(device, peaks)          # BASELINE configs[2]
+            also["sppp_sweep"] = sppp_sweep(device, peaks)
+        # BASELINE configs[4]: every rank runs its 32-image share of the high-resolution inference batch
+        import torch.distributed as dist
+        also["sppp_vits_mhla_512_infer"] = run_infer(device, 20, 3, rank, world, world > 1)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        out["also"] = also
     if rank == 0:
         print(json.dumps(out), flush=True)
 

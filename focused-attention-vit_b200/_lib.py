@@ -31,6 +31,10 @@ _SIGS = {
                              _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
     "favit_linear_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp], _i),
     "favit_linear_dgrad": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp], _i),
+    "favit_linear_fwd_dropout": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _f, _vp,
+                                  _u64, _vp], _i),
+    "favit_linear_dgrad_dropout": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _f, _vp, _u64, _vp], _i),
+    "favit_dropout_cast": ([_vp, _vp, _i, _vp, _i, _i, _f, _vp, _u64, _vp], _i),
     "favit_linear_wgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp], _i),
     "favit_gemm_bf16_raw": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp], _i),
     "favit_latent_fold_fwd": ([_vp] * 10 + [_i, _i, _i, _vp], _i),

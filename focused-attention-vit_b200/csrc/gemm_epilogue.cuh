@@ -53,4 +53,36 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return fmaf(x * kp, t, P);
 }
 
+// ---- MLP dropout (models/vit.py:122,125-139: nn.Dropout after the activation and after fc2) -----------------------------
+// Counter-based keep-mask, regenerated in backward instead of stored: element (row, col) of an [M, N] tensor belongs to
+// group g = row * ceil(N / 4) + col / 4; one splitmix64 of key + g * golden gives four 16-bit uniforms, lane col % 4 is
+// kept iff it is >= thr = round(p * 65536) and the kept value is scaled by 1 / (1 - thr / 65536).  key = *seed + offset:
+// the seed lives in device memory so that a captured CUDA graph draws a fresh mask on every replay, the offset tells
+// layers and dropout sites apart.  oracle/mhla_oracle.py:mlp_dropout_keep_mask reproduces it bit for bit.
+struct DropSpec {
+  const unsigned long long* seed = nullptr;  // device pointer; nullptr = no dropout
+  unsigned long long offset = 0;
+  unsigned thr = 0;       // drop iff u16 < thr
+  float inv_keep = 1.f;
+  int groups_per_row = 0;
+};
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// v[0..31] = columns col..col+31 (col % 4 == 0) of row `row`
+__device__ __forceinline__ void dropout32(float (&v)[32], unsigned long long key, int row, int col, const DropSpec& d) {
+  const unsigned long long g0 = (unsigned long long)row * (unsigned long long)d.groups_per_row + (unsigned)(col >> 2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const unsigned long long z = splitmix64(key + (g0 + j) * 0x9E3779B97F4A7C15ull);
+    const unsigned lo = (unsigned)z, hi = (unsigned)(z >> 32);
+    v[4 * j] = (lo & 0xffffu) >= d.thr ? v[4 * j] * d.inv_keep : 0.f;
+    v[4 * j + 1] = (lo >> 16) >= d.thr ? v[4 * j + 1] * d.inv_keep : 0.f;
+    v[4 * j + 2] = (hi & 0xffffu) >= d.thr ? v[4 * j + 2] * d.inv_keep : 0.f;
+    v[4 * j + 3] = (hi >> 16) >= d.thr ? v[4 * j + 3] * d.inv_keep : 0.f;
+  }
+}
+
 }  // namespace favit

@@ -412,6 +412,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int o_vec = e.aux_out ? vec_ok(e.aux_out, FAVIT_BF16, e.ldaux) : 0;
     const bool b_vec = e.bias ? (((uintptr_t)e.bias) % 16 == 0) : false;
     const bool atomic = (p.splits > 1) || e.accumulate;
+    const unsigned long long drop_key = e.drop.seed ? __ldg(e.drop.seed) + e.drop.offset : 0ull;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int tile = u / p.splits;
       const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
@@ -468,6 +469,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] *= dgelu_fast(x[i]);
             }
+            if (e.drop.seed) dropout32(v, drop_key, row, col, e.drop);
             if (e.residual) {
               float x[32];
               load32(e.residual, e.res_dtype, (int64_t)row * e.ldres + col, full ? r_vec : 0, ncols, x);

@@ -3,12 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gemm_epilogue.cuh"
+
 namespace favit {
 namespace tc {
 
 // What happens to an fp32 accumulator tile on its way out of TMEM.
 //   v = acc (+ bias[col]);  act: GELU (optionally saving the pre-activation), or v *= gelu'(aux);
-//   v += residual[row,col];  C[row,col] = v   (or atomically C += v when accumulate / split-K).
+//   v *= dropout keep-mask / (1 - p);  v += residual[row,col];  C[row,col] = v   (or atomically C += v when accumulate / split-K).
 struct Epilogue {
   void* c = nullptr;
   int64_t ldc = 0;
@@ -24,6 +26,7 @@ struct Epilogue {
   int accumulate = 0;             // C += result (fp32 C only)
   int split_ok = 0;               // caller allows split-K (C is zeroed or being accumulated into)
   float* colsum = nullptr;        // [N] fp32, accumulated: column sums of a bf16 C (CTA-pair kernel only)
+  DropSpec drop;                  // dropout applied after `act`, before the residual (drop.seed == nullptr: none)
 };
 
 // C[M,N] = A.B^T with the operand storage flags described in gemm_tcgen05.cu.

@@ -55,6 +55,7 @@ struct K2Params {
   int c_fp32;    // C element type: 1 = fp32 (box 32 x 32), 0 = bf16 (box 64 x 32)
   int reduce;    // accumulate into C with TMA reduce-add (split-K or accumulate)
   float* colsum; // [N] fp32, accumulated: column sums of the bf16 output (plain / GELU' epilogues only)
+  DropSpec drop; // keep-mask applied after the activation (GELU: to the activation only, not to the saved pre-activation)
 };
 
 // this lane's 32-column slice -> its row of a swizzled staging unit (bf16: 4 x 16-byte chunks at chunk offset `c4`)
@@ -221,6 +222,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     uint8_t* auxbuf = smem_gen + (aux_base - smem_base) + ew * 2 * kUnit;
     const uint32_t auxbuf_u32 = aux_base + ew * 2 * kUnit;
     const bool b_vec = p.bias ? (((uintptr_t)p.bias) % 16 == 0) : false;
+    const unsigned long long drop_key = p.drop.seed ? __ldg(p.drop.seed) + p.drop.offset : 0ull;
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     int obuf = 0;  // next staging buffer (round robin)
@@ -262,6 +264,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
           }
         }
+        if (p.drop.seed && p.act != FAVIT_EPI_GELU && !AUX && !p.reduce) dropout32(v, drop_key, row0 + lane, col, p.drop);
         if (p.c_fp32) {
           // one staging unit per 32 columns
           uint8_t* ub = outbuf + obuf * kUnit;
@@ -295,6 +298,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          if (p.drop.seed) dropout32(v, drop_key, row0 + lane, col, p.drop);
           if ((c & 1) == 0) {
             if (lane == 0) tma_store_wait_read<0>();  // ... and its activation store has read buffer 1
             __syncwarp();
@@ -314,6 +318,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             unstage_bf16(auxbuf + (c >> 1) * kUnit, lane, (c & 1) * 4, x);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= dgelu_fast(x[i]);
+            if (p.drop.seed) dropout32(v, drop_key, row0 + lane, col, p.drop);
           }
           uint8_t* ub = outbuf + obuf * kUnit;
           if ((c & 1) == 0) {
@@ -510,6 +515,7 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.c_fp32 = c_fp32 ? 1 : 0;
   kp.reduce = (splits > 1 || epi.accumulate) ? 1 : 0;
   kp.colsum = epi.colsum;
+  kp.drop = epi.drop;
   const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
   note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d", aux ? 1 : 0,
               kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn);

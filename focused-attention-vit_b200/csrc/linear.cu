@@ -70,6 +70,73 @@ int launch_colsum(const void* dy, float* db, int M, int N, int64_t ld, cudaStrea
   return FAVIT_OK;
 }
 
+// DropSpec for an [rows, cols] output: p quantised to 16 bits, 4 columns per hash (gemm_epilogue.cuh)
+int make_drop(const char* who, float p, const unsigned long long* seed, unsigned long long offset, int cols, DropSpec* d) {
+  *d = DropSpec();
+  if (p <= 0.f) return FAVIT_OK;
+  FAVIT_CHECK_ARG(p < 1.f && seed, "%s: dropout needs 0 <= p < 1 and a device seed pointer (p = %g)", who, (double)p);
+  d->thr = (unsigned)lrintf(p * 65536.f);
+  if (d->thr == 0) return FAVIT_OK;  // p below 2^-17: nothing is ever dropped
+  d->seed = seed;
+  d->offset = offset;
+  d->inv_keep = 65536.f / (float)(65536u - d->thr);
+  d->groups_per_row = (cols + 3) / 4;
+  return FAVIT_OK;
+}
+
+// out[m, n] = keep(m, n) ? g[m, n] / (1 - p) : 0 in the compute dtype, plus the fp32 column sums of `out` as stored:
+// the gradient entering fc2 (models/vit.py:132-138: the dropout after fc2 masks it) as a GEMM operand, and fc2's bias
+// gradient.  One thread owns 8 consecutive columns of a strip of rows.
+template <typename TOut>
+__global__ void __launch_bounds__(256) dropout_cast_kernel(const float* __restrict__ g, TOut* __restrict__ out,
+                                                           float* __restrict__ colsum, int M, int N, int rows_per_cta,
+                                                           const DropSpec d) {
+  __shared__ float s_part[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const unsigned long long key = d.seed ? __ldg(d.seed) + d.offset : 0ull;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < N) {   // N % 8 == 0 (checked by the host)
+    for (int r = r0 + warp; r < r1; r += 8) {
+      float f[8];
+      load8(g + (int64_t)r * N + c0, f);
+      if (d.seed) {
+        const unsigned long long g0 = (unsigned long long)r * (unsigned long long)d.groups_per_row + (unsigned)(c0 >> 2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const unsigned long long z = splitmix64(key + (g0 + j) * 0x9E3779B97F4A7C15ull);
+          const unsigned lo = (unsigned)z, hi = (unsigned)(z >> 32);
+          f[4 * j] = (lo & 0xffffu) >= d.thr ? f[4 * j] * d.inv_keep : 0.f;
+          f[4 * j + 1] = (lo >> 16) >= d.thr ? f[4 * j + 1] * d.inv_keep : 0.f;
+          f[4 * j + 2] = (hi & 0xffffu) >= d.thr ? f[4 * j + 2] * d.inv_keep : 0.f;
+          f[4 * j + 3] = (hi >> 16) >= d.thr ? f[4 * j + 3] * d.inv_keep : 0.f;
+        }
+      }
+      store8(out + (int64_t)r * N + c0, f);
+      if constexpr (sizeof(TOut) == 2) {   // sum what was stored (bf16-rounded), like the GEMM-epilogue column sums
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+  if (!colsum) return;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_part[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w][threadIdx.x];
+    atomicAdd(colsum + c, s);
+  }
+}
+
 int check_dims(const char* who, int M, int N, int K) {
   FAVIT_CHECK_ARG(M > 0 && N > 0 && K > 0, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
   return FAVIT_OK;
@@ -84,11 +151,21 @@ extern "C" int favit_linear_fwd(const void* x, const void* w, const float* bias,
                                 void* preact_out, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
                                 int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
                                 int epilogue, favit_stream stream) {
+  return favit_linear_fwd_dropout(x, w, bias, residual, y, preact_out, M, N, K, ldx, ldw, ldy, ldres, dtype, y_dtype,
+                                  res_dtype, epilogue, 0.f, nullptr, 0, stream);
+}
+
+extern "C" int favit_linear_fwd_dropout(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                        void* preact_out, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                                        int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
+                                        int epilogue, float drop_p, const uint64_t* drop_seed, uint64_t drop_offset,
+                                        favit_stream stream) {
   if (int rc = check_dims("linear_fwd", M, N, K)) return rc;
   FAVIT_CHECK_ARG(x && w && y, "linear_fwd: null x/w/y");
   FAVIT_CHECK_ARG(epilogue == FAVIT_EPI_NONE || epilogue == FAVIT_EPI_GELU, "linear_fwd: bad epilogue %d", epilogue);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FAVIT_F32) {
+    FAVIT_CHECK_ARG(drop_p <= 0.f, "linear_fwd: the fused dropout epilogue exists on the bf16 path only");
     FAVIT_CHECK_ARG(y_dtype == FAVIT_F32 && (!residual || res_dtype == FAVIT_F32),
                     "linear_fwd: the fp32 path is fp32 end to end");
     return gemm_simt_launch((const float*)x, (const float*)w, (float*)y, bias, nullptr, (float*)preact_out,
@@ -101,12 +178,21 @@ extern "C" int favit_linear_fwd(const void* x, const void* w, const float* bias,
   e.residual = residual; e.ldres = ldres; e.res_dtype = res_dtype;
   e.aux_out = preact_out; e.ldaux = ldy;
   e.act = epilogue;
+  if (int rc = make_drop("linear_fwd", drop_p, (const unsigned long long*)drop_seed, drop_offset, N, &e.drop)) return rc;
   return tc::gemm_bf16(x, 0, ldx, w, 0, ldw, M, N, K, e, 0, 0, st);
 }
 
 extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* preact, void* dx, float* dx_colsum, int M,
                                   int N, int K, int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype,
                                   favit_dtype dx_dtype, int epilogue, favit_stream stream) {
+  return favit_linear_dgrad_dropout(dy, w, preact, dx, dx_colsum, M, N, K, lddy, ldw, lddx, dtype, dx_dtype, epilogue,
+                                    0.f, nullptr, 0, stream);
+}
+
+extern "C" int favit_linear_dgrad_dropout(const void* dy, const void* w, const void* preact, void* dx, float* dx_colsum,
+                                          int M, int N, int K, int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype,
+                                          favit_dtype dx_dtype, int epilogue, float drop_p, const uint64_t* drop_seed,
+                                          uint64_t drop_offset, favit_stream stream) {
   if (int rc = check_dims("linear_dgrad", M, N, K)) return rc;
   FAVIT_CHECK_ARG(dy && w && dx, "linear_dgrad: null dy/w/dx");
   FAVIT_CHECK_ARG(epilogue == FAVIT_EPI_NONE || (epilogue == FAVIT_EPI_DGELU_MUL && preact),
@@ -114,6 +200,7 @@ extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* pre
   cudaStream_t st = (cudaStream_t)stream;
   // dX[m,k] = sum_n dY[m,n] W[n,k]: output M x K, reduction over N; W is stored [reduction][out] (MN-major B)
   if (dtype == FAVIT_F32) {
+    FAVIT_CHECK_ARG(drop_p <= 0.f, "linear_dgrad: the fused dropout epilogue exists on the bf16 path only");
     FAVIT_CHECK_ARG(dx_dtype == FAVIT_F32, "linear_dgrad: the fp32 path is fp32 end to end");
     int rc = gemm_simt_launch((const float*)dy, (const float*)w, (float*)dx, nullptr, (const float*)preact, nullptr,
                               nullptr, 0, M, K, N, lddy, 1, 1, ldw, lddx, epilogue, 1, 0, st);
@@ -125,6 +212,7 @@ extern "C" int favit_linear_dgrad(const void* dy, const void* w, const void* pre
   e.c = dx; e.ldc = lddx; e.c_dtype = dx_dtype;
   e.aux = preact; e.ldaux = lddx;
   e.act = epilogue;
+  if (int rc = make_drop("linear_dgrad", drop_p, (const unsigned long long*)drop_seed, drop_offset, K, &e.drop)) return rc;
   // the CTA-pair kernel sums the columns of dX in its epilogue; otherwise one extra pass over dX
   e.colsum = dx_colsum;
   const bool fused = dx_colsum && tc::gemm_bf16_2cta_applicable(M, K, N, e, lddy, ldw);
@@ -243,4 +331,27 @@ extern "C" int favit_colsum(const void* x, favit_dtype dtype, float* out, int M,
   if (dtype == FAVIT_BF16) return launch_colsum<__nv_bfloat16>(x, out, M, N, ld, (cudaStream_t)stream);
   set_error("colsum: bad dtype");
   return FAVIT_ERR_ARG;
+}
+
+// out = dropout-masked, rescaled copy of the fp32 gradient g in the compute dtype (+ accumulated fp32 column sums)
+extern "C" int favit_dropout_cast(const float* g, void* out, favit_dtype out_dtype, float* colsum, int M, int N,
+                                  float drop_p, const uint64_t* drop_seed, uint64_t drop_offset, favit_stream stream) {
+  FAVIT_CHECK_ARG(g && out && M > 0 && N > 0, "dropout_cast: bad argument");
+  FAVIT_CHECK_ARG(N % 8 == 0 && ((uintptr_t)g % 16 == 0) && ((uintptr_t)out % 16 == 0),
+                  "dropout_cast: N must be a multiple of 8 and the tensors 16-byte aligned");
+  DropSpec d;
+  if (int rc = make_drop("dropout_cast", drop_p, (const unsigned long long*)drop_seed, drop_offset, N, &d)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int col_blocks = ceil_div(N, 256);
+  int row_blocks = max(1, min(ceil_div(M, 32), ceil_div(8 * num_sms(), col_blocks)));
+  const int rows_per_cta = ceil_div(ceil_div(M, row_blocks), 8) * 8;
+  row_blocks = ceil_div(M, rows_per_cta);
+  if (out_dtype == FAVIT_BF16)
+    dropout_cast_kernel<__nv_bfloat16><<<dim3(col_blocks, row_blocks), 256, 0, st>>>(g, (__nv_bfloat16*)out, colsum, M, N,
+                                                                                  rows_per_cta, d);
+  else if (out_dtype == FAVIT_F32)
+    dropout_cast_kernel<float><<<dim3(col_blocks, row_blocks), 256, 0, st>>>(g, (float*)out, colsum, M, N, rows_per_cta, d);
+  else { set_error("dropout_cast: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
 }

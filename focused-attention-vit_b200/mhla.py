@@ -85,6 +85,7 @@ class MultiHeadLatentAttention(nn.Module):
             raise RuntimeError(f"stack expects each tensor to be equal size: even window_size={W} with "
                                f"seq_len={N} > window_size is ragged (reference models/mhla.py:83)")
         cd = compute_dtype(x)
+        self._check_supported(x, cd)
         if self.training and self.attn_dropout.p > 0:
             return self._forward_attn_dropout(x, attention_mask, cd)
         with torch.autocast("cuda", enabled=False):
@@ -100,12 +101,33 @@ class MultiHeadLatentAttention(nn.Module):
             y = ops.linear(out.reshape(B * N, D), pw, pb).view(B, N, D)
         return self.proj_dropout(y)
 
+    def _check_supported(self, x: torch.Tensor, cd: torch.dtype) -> None:
+        """The limits of the favit kernels, named up front (INTEGRATION.md lists them) instead of failing inside a kernel
+        wrapper: the reference itself runs any dtype / head_dim on eager PyTorch."""
+        if not x.is_cuda:
+            raise RuntimeError("favit MultiHeadLatentAttention runs on CUDA tensors only (sm_100a kernels; there is no "
+                               "CPU fallback)")
+        if cd not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"favit MultiHeadLatentAttention computes in float32 or bfloat16 (bf16 autocast), got {cd}: "
+                            "float16 / float64 inputs and fp16 autocast are not supported")
+        if self.head_dim not in (16, 32, 64, 128):
+            raise ValueError(f"favit MultiHeadLatentAttention supports head_dim 16, 32, 64 or 128, got {self.head_dim} "
+                             f"(embed_dim {self.embed_dim} / num_heads {self.num_heads})")
+        if cd == torch.bfloat16 and self.embed_dim % 8:
+            raise ValueError(f"favit MultiHeadLatentAttention needs embed_dim % 8 == 0 in bf16 (TMA row pitch), got "
+                             f"{self.embed_dim}")
+
     def _forward_attn_dropout(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor], cd) -> torch.Tensor:
         """Training with attention-probability dropout p > 0 (mhla.py:147).  The K-side fold of latent_proj stays valid
         (its bias term is constant along the softmax axis and dropout comes after the softmax); the V-side fold does
         not, because dropped rows of probabilities no longer sum to one, so V gets its latent projection explicitly as
         in mhla.py:106 and proj keeps its own weights.  Statistical parity with the reference: the keep-mask comes from
         favit's counter-based generator, one Bernoulli per window slot like nn.Dropout on the [B,H,N,W] probabilities."""
+        if torch.cuda.is_current_stream_capturing():
+            # the keep-mask seed of the attention kernels is a host value baked into the launch arguments: a captured
+            # graph would replay the same mask on every step (nn.Dropout stays random under capture)
+            raise RuntimeError("attention-probability dropout (attn_dropout > 0 in training mode) cannot be captured in a "
+                               "CUDA graph: use engine.TrainStep(cuda_graph=False) or attn_dropout=0.0")
         B, N, D = x.shape
         H, hd, W = self.num_heads, self.head_dim, self.window_size
         p = float(self.attn_dropout.p)
@@ -129,7 +151,7 @@ class MultiHeadLatentAttention(nn.Module):
 
 def _dropout_seed() -> int:
     """One 62-bit seed per forward from torch's CPU generator (reproducible under torch.manual_seed).  It is a host
-    value: a captured CUDA graph would replay the same mask, so train with cuda_graph=False when p > 0."""
+    value: `_forward_attn_dropout` refuses to run under CUDA-graph capture, where it would be frozen."""
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
@@ -158,7 +180,8 @@ class MHLATransformerBlock(nn.Module):
         if fused_block.fusable(x, self.attn, self.mlp[2].p, self.training, attention_mask, cd,
                                self.mlp[0].out_features):
             with torch.autocast("cuda", enabled=False):
-                return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp[0], self.mlp[3], cd)
+                return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp[0], self.mlp[3], cd,
+                                               self.mlp[2].p if self.training else 0.0)
         x = x + self.attn(self.norm1(x), attention_mask)
         x = x + self.mlp(self.norm2(x))
         return x

@@ -91,7 +91,8 @@ class TransformerBlock(nn.Module):
                                    self.mlp.fc1.out_features):
                 # whole block as two favit ops (LN, GEMMs with fused bias/GELU/residual, window attention)
                 with torch.autocast("cuda", enabled=False):
-                    return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp.fc1, self.mlp.fc2, cd)
+                    return fused_block.fused_block(x, self.norm1, self.attn, self.norm2, self.mlp.fc1, self.mlp.fc2, cd,
+                                                   self.mlp.dropout.p if self.training else 0.0)
         x_norm = self.norm1(x)
         if self.use_mhla:
             attn_output = self.attn(x_norm, attention_mask)
@@ -112,10 +113,11 @@ def run_blocks(blocks, x: torch.Tensor) -> torch.Tensor:
     if a0 is not None and len(blks) > 1 and all(
             isinstance(b, TransformerBlock) and b.use_mhla and b.attn.num_heads == a0.num_heads and
             b.attn.window_size == a0.window_size and b.attn.embed_dim == a0.embed_dim and
+            b.mlp.dropout.p == blks[0].mlp.dropout.p and b.training == blks[0].training and
             fused_block.fusable(x, b.attn, b.mlp.dropout.p, b.training, None, cd, b.mlp.fc1.out_features)
             for b in blks):
         with torch.autocast("cuda", enabled=False):
-            return fused_block.run_blocks(blks, x, cd)
+            return fused_block.run_blocks(blks, x, cd, blks[0].mlp.dropout.p if blks[0].training else 0.0)
     for block in blks:
         x = block(x)
     return x

@@ -20,30 +20,54 @@ def _p(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# layers / dropout sites of one forward call draw from the same device seed at different offsets
+_DROP_STRIDE = 0xD1B54A32D192ED03
+
+
+def drop_offset(layer: int, site: int) -> int:
+    """site 1 = the dropout after the activation, site 2 = the dropout after fc2 (models/vit.py:131-138)."""
+    return ((2 * layer + site) * _DROP_STRIDE) & 0xFFFFFFFFFFFFFFFF
+
+
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], out_dtype: torch.dtype,
-               gelu: bool = False, save_preact: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+               gelu: bool = False, save_preact: bool = False, drop=None) -> Tuple[Tensor, Optional[Tensor]]:
+    """drop = (p, seed int64[1] device tensor, offset): dropout fused behind the activation (favit_linear_fwd_dropout)."""
     M, K = x.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=out_dtype, device=x.device)
     pre = torch.empty((M, N), dtype=x.dtype, device=x.device) if (gelu and save_preact) else None
-    rc = L.call("gemm_fwd", 2.0 * M * N * K, L.lib().favit_linear_fwd, _p(x), _p(w), _p(bias), _p(residual), _p(y),
+    p_, seed_, off_ = drop if drop is not None else (0.0, None, 0)
+    rc = L.call("gemm_fwd", 2.0 * M * N * K, L.lib().favit_linear_fwd_dropout, _p(x), _p(w), _p(bias), _p(residual), _p(y),
                 _p(pre), M, N, K, K, K, N, N, _DT[x.dtype], _DT[out_dtype],
-                _DT[residual.dtype] if residual is not None else L.F32, L.EPI_GELU if gelu else L.EPI_NONE, _s())
+                _DT[residual.dtype] if residual is not None else L.F32, L.EPI_GELU if gelu else L.EPI_NONE,
+                float(p_), _p(seed_), off_, _s())
     L.check(rc, "favit_linear_fwd")
     return y, pre
 
 
+def dropout_cast(g: Tensor, out_dtype: torch.dtype, drop, colsum: Optional[Tensor] = None) -> Tensor:
+    """keep / (1 - p) * g (fp32 [M,N]) in out_dtype; `colsum` (already zeroed fp32 [N]) receives the column sums."""
+    M, N = g.shape
+    out = torch.empty((M, N), dtype=out_dtype, device=g.device)
+    p_, seed_, off_ = drop
+    rc = L.call("dropout_cast", float(g.numel() * (4 + out.element_size())), L.lib().favit_dropout_cast, _p(g), _p(out),
+                _DT[out_dtype], _p(colsum), M, N, float(p_), _p(seed_), off_, _s())
+    L.check(rc, "favit_dropout_cast")
+    return out
+
+
 def linear_dgrad(dy: Tensor, w: Tensor, preact: Optional[Tensor], out_dtype: torch.dtype, colsum: bool = False,
-                 zeroed: Optional[Tensor] = None):
+                 zeroed: Optional[Tensor] = None, drop=None):
     """dx = dy @ w (* gelu'(preact)); with colsum also the fp32 column sums of dx (returns (dx, sums)).
     `zeroed`: an already zeroed fp32 [K] buffer to accumulate the column sums into (saves a fill launch)."""
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
     sums = (zeroed if zeroed is not None else torch.zeros((K,), dtype=torch.float32, device=dy.device)) if colsum else None
-    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad, _p(dy), _p(w), _p(preact), _p(dx), _p(sums),
-                M, N, K, N, K, K, _DT[dy.dtype], _DT[out_dtype],
-                L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, _s())
+    p_, seed_, off_ = drop if drop is not None else (0.0, None, 0)
+    rc = L.call("gemm_dgrad", 2.0 * M * N * K, L.lib().favit_linear_dgrad_dropout, _p(dy), _p(w), _p(preact), _p(dx),
+                _p(sums), M, N, K, N, K, K, _DT[dy.dtype], _DT[out_dtype],
+                L.EPI_DGELU_MUL if preact is not None else L.EPI_NONE, float(p_), _p(seed_), off_, _s())
     L.check(rc, "favit_linear_dgrad")
     return (dx, sums) if colsum else dx
 

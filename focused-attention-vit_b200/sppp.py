@@ -47,8 +47,44 @@ class SuperpixelAssignment:
 
 class AssignmentDict(dict):
     """The dict `map_patches` returns; remembers the device arrays it was built from so `pool` need not rebuild
-    them."""
+    them.  Any mutation (the reference API allows callers to drop, merge or pad superpixels before pooling) forgets
+    them, and `pool` then rebuilds the CSR from the dict's current contents."""
     assignment: Optional[SuperpixelAssignment] = None
+
+    def _touch(self):
+        self.assignment = None
+
+    def __setitem__(self, k, v):
+        self._touch()
+        super().__setitem__(k, v)
+
+    def __delitem__(self, k):
+        self._touch()
+        super().__delitem__(k)
+
+    def pop(self, *a):
+        self._touch()
+        return super().pop(*a)
+
+    def popitem(self):
+        self._touch()
+        return super().popitem()
+
+    def update(self, *a, **k):
+        self._touch()
+        super().update(*a, **k)
+
+    def setdefault(self, k, d=None):
+        self._touch()
+        return super().setdefault(k, d)
+
+    def clear(self):
+        self._touch()
+        super().clear()
+
+    def __ior__(self, other):
+        self._touch()
+        return super().__ior__(other)
 
 
 class PatchToSuperpixelMapper:
@@ -73,6 +109,7 @@ class PatchToSuperpixelMapper:
         a = self.assign_batch(segmentation_map.unsqueeze(0), img_size)
         d = a.to_dicts()[0]
         d.assignment = a
+        d._sizes = [len(v) for v in d.values()]
         return d
 
 
@@ -90,6 +127,8 @@ def _assignment_from_dict(d: Dict[int, List[int]], num_patches: int, device) -> 
         counts[0, r] = len(patches)
         offsets[0, r + 1] = offsets[0, r] + len(patches)
         for p in patches:
+            if not 0 <= int(p) < num_patches:      # the reference's fancy indexing raises IndexError here (sppp.py:209)
+                raise IndexError(f"index {int(p)} is out of bounds for dimension 0 with size {num_patches}")
             slot[0, p] = r
         flat.extend(int(p) for p in patches)
     offsets[0, R + 1:] = offsets[0, R]
@@ -138,6 +177,12 @@ class SuperpixelPooling:
         xb = x if batched else x.unsqueeze(0)
         B, P, D = xb.shape
         a = getattr(superpixel_to_patches, "assignment", None)
+        if a is not None:
+            # the lists inside the dict can be edited in place without the dict noticing: the cached arrays are reused
+            # only if the dict still has the sizes they were built from
+            sizes = getattr(superpixel_to_patches, "_sizes", None)
+            if sizes != [len(v) for v in superpixel_to_patches.values()]:
+                a = None
         if a is None or a.slot.shape[1] != P or a.slot.device != x.device:
             a = _assignment_from_dict(superpixel_to_patches, P, x.device)
         R = len(superpixel_to_patches)

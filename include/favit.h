@@ -119,6 +119,31 @@ int favit_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int 
                        int64_t lddy, int64_t ldx, int64_t lddw, favit_dtype dtype, int accumulate,
                        favit_stream stream);
 
+/* The same two entry points with the MLP's nn.Dropout (models/vit.py:122, 131-138; main.py:106 `--dropout 0.1`) fused into
+ * the epilogue, bf16 path only: after the activation and before the residual the value is multiplied by
+ * keep(row, col) / (1 - p).  The keep-mask is counter based and is REGENERATED in backward, never stored: element
+ * (row, col) of an [M, N] result belongs to group g = row * ceil(N / 4) + col / 4; splitmix64(*drop_seed + drop_offset +
+ * g * 0x9E3779B97F4A7C15) yields four 16-bit uniforms, lane col % 4 is kept iff it is >= round(p * 65536).  drop_seed is a
+ * DEVICE pointer (a captured CUDA graph draws a fresh mask per replay when the caller bumps it in-stream), drop_offset
+ * tells layers / sites apart.  The reference draws its mask from torch's Philox stream, so only the distribution is
+ * the reference's; oracle/mhla_oracle.py:mlp_dropout_keep_mask reproduces this generator bit for bit.
+ *   fwd  : Y = dropout(act(X.W^T + bias)) + residual   (GELU: the saved pre-activation is NOT masked)
+ *   dgrad: dX = (dY.W) * gelu'(preact) * keep / (1 - p)   — the mask of the dropout that followed the activation */
+int favit_linear_fwd_dropout(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                             void* preact_out, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                             int64_t ldres, favit_dtype dtype, favit_dtype y_dtype, favit_dtype res_dtype,
+                             int epilogue, float drop_p, const uint64_t* drop_seed, uint64_t drop_offset,
+                             favit_stream stream);
+int favit_linear_dgrad_dropout(const void* dy, const void* w, const void* preact, void* dx, float* dx_colsum, int M,
+                               int N, int K, int64_t lddy, int64_t ldw, int64_t lddx, favit_dtype dtype,
+                               favit_dtype dx_dtype, int epilogue, float drop_p, const uint64_t* drop_seed,
+                               uint64_t drop_offset, favit_stream stream);
+/* out[M,N] (fp32 or bf16, contiguous) = keep / (1 - p) * g[M,N] (fp32) with the mask above, and colsum[N] (may be NULL,
+ * ACCUMULATED) += column sums of out: the gradient that enters fc2 behind its dropout (vit.py:138) as a GEMM operand,
+ * and fc2's bias gradient.  N % 8 == 0. */
+int favit_dropout_cast(const float* g, void* out, favit_dtype out_dtype, float* colsum, int M, int N, float drop_p,
+                       const uint64_t* drop_seed, uint64_t drop_offset, favit_stream stream);
+
 /* out[n] += sum over the M rows of x[m,n] (x row-major with leading dimension ld): a bias gradient. */
 int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int64_t ld, favit_stream stream);
 

@@ -22,6 +22,7 @@ from .mhla_oracle import (  # noqa: F401
     mhla_attn_core_closed_form,
     mhla_attn_core_gather,
     dropout_keep_mask,
+    mlp_dropout_keep_mask,
     fold_latent,
 )
 from .models_oracle import (  # noqa: F401

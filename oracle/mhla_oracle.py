@@ -117,6 +117,25 @@ def dropout_keep_mask(B: int, H: int, N: int, W: int, p: float, seed: int) -> np
     return (u >= np.float32(p)).reshape(B, H, N, W)
 
 
+def mlp_dropout_keep_mask(M: int, N: int, p: float, seed: int, layer: int, site: int):
+    """(keep bool [M,N], inv_keep) of the fused MLP dropout (include/favit.h: favit_linear_fwd_dropout): element (row, col)
+    belongs to group g = row * ceil(N/4) + col // 4; splitmix64(seed + offset(layer, site) + g * golden) gives four 16-bit
+    uniforms; lane col % 4 is kept iff it is >= thr = round(p * 65536); kept values are scaled by 65536 / (65536 - thr).
+    site 1 = after the activation, site 2 = after fc2 (models/vit.py:131-138).  The reference draws from torch's Philox
+    stream: only the distribution is the reference's; this pins the kernels' mask bit for bit."""
+    thr = int(np.rint(np.float32(p) * np.float32(65536.0)))
+    gpr = (N + 3) // 4
+    offset = ((2 * layer + site) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    g = (np.arange(M, dtype=np.uint64)[:, None] * np.uint64(gpr) + np.arange(gpr, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + np.uint64(offset) + g * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    lanes = np.stack([(z >> np.uint64(16 * t)) & np.uint64(0xFFFF) for t in range(4)], axis=-1).reshape(M, gpr * 4)[:, :N]
+    return lanes >= np.uint64(thr), 65536.0 / (65536.0 - thr)
+
+
 def mhla_attn_core_gather(q, k, v, window_size: int, attention_mask: Optional[torch.Tensor] = None,
                           keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0) -> torch.Tensor:
     """The attention core in the reference's own formulation (mhla.py:109-154): window gather, scaled scores, mask,

@@ -31,8 +31,13 @@ def patch_embed(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, ps: int) -> t
     return F.linear(t, w, b)
 
 
-def block(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, num_heads: int, window: int) -> torch.Tensor:
-    """TransformerBlock.forward with use_mhla=True and dropout 0 (models/vit_mhla.py:77-109)."""
+def block(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, num_heads: int, window: int,
+          mlp_dropout: float = 0.0, masks=None) -> torch.Tensor:
+    """TransformerBlock.forward with use_mhla=True (models/vit_mhla.py:77-109).  mlp_dropout > 0 = training mode of
+    models/vit.py:125-139 (dropout after the activation and after fc2) with torch's own generator: only the
+    distribution is the reference's, so parity tests keep it at 0 and only the main.py-style CPU timing arm uses it.
+    masks = (keep1 [B*N, hidden], keep2 [B*N, D], inv_keep): the two dropouts with EXPLICIT keep-masks (those of favit's
+    counter-based generator, oracle.mlp_dropout_keep_mask), for exact parity of the fused dropout epilogues."""
     D = x.shape[-1]
     xn = F.layer_norm(x, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
     a = mhla_forward_gather(xn, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"], sd[pre + "attn.proj.weight"],
@@ -44,8 +49,13 @@ def block(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, num_heads: int
         k1, k2 = "mlp.fc1.", "mlp.fc2."
     else:                                  # nn.Sequential of MHLATransformerBlock (models/mhla.py:197-203)
         k1, k2 = "mlp.0.", "mlp.3."
-    h = F.gelu(F.linear(xn, sd[pre + k1 + "weight"], sd[pre + k1 + "bias"]))
-    return x + F.linear(h, sd[pre + k2 + "weight"], sd[pre + k2 + "bias"])
+    if masks is not None:
+        k1m, k2m, inv = masks
+        B, N = x.shape[0], x.shape[1]
+        h = F.gelu(F.linear(xn, sd[pre + k1 + "weight"], sd[pre + k1 + "bias"])) * (k1m.view(B, N, -1).to(x.dtype) * inv)
+        return x + F.linear(h, sd[pre + k2 + "weight"], sd[pre + k2 + "bias"]) * (k2m.view(B, N, -1).to(x.dtype) * inv)
+    h = F.dropout(F.gelu(F.linear(xn, sd[pre + k1 + "weight"], sd[pre + k1 + "bias"])), mlp_dropout, mlp_dropout > 0)
+    return x + F.dropout(F.linear(h, sd[pre + k2 + "weight"], sd[pre + k2 + "bias"]), mlp_dropout, mlp_dropout > 0)
 
 
 def _depth(sd) -> int:
@@ -53,12 +63,12 @@ def _depth(sd) -> int:
 
 
 def vit_mhla_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], patch_size: int, num_heads: int,
-                     window: int) -> torch.Tensor:
+                     window: int, mlp_dropout: float = 0.0) -> torch.Tensor:
     B = x.shape[0]
     t = patch_embed(x, sd["patch_embed.projection.1.weight"], sd["patch_embed.projection.1.bias"], patch_size)
     t = torch.cat((sd["cls_token"].expand(B, -1, -1), t), dim=1) + sd["pos_embed"]
     for i in range(_depth(sd)):
-        t = block(t, sd, f"blocks.{i}.", num_heads, window)
+        t = block(t, sd, f"blocks.{i}.", num_heads, window, mlp_dropout)
     D = t.shape[-1]
     t = F.layer_norm(t, (D,), sd["norm.weight"], sd["norm.bias"])
     return F.linear(t[:, 0], sd["head.weight"], sd["head.bias"])

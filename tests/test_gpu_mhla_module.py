@@ -79,3 +79,29 @@ def test_constructor_contract():
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 9, 64, device="cuda"))
     assert list(dict(m.named_parameters())) == PARAMS
+
+
+def test_unsupported_configurations_are_named_up_front():
+    """INTEGRATION.md 'Limits': the favit path raises one clear error at the module boundary."""
+    import pytest
+    import torch
+    from favit_b200.mhla import MultiHeadLatentAttention
+    m = MultiHeadLatentAttention(embed_dim=96, num_heads=2).cuda()            # head_dim 48
+    with pytest.raises(ValueError, match="head_dim"):
+        m(torch.randn(1, 9, 96, device="cuda"))
+    m = MultiHeadLatentAttention(embed_dim=64, num_heads=2).cuda()
+    with pytest.raises(TypeError, match="float32 or bfloat16"):
+        m.half()(torch.randn(1, 9, 64, device="cuda").half())
+    with pytest.raises(TypeError, match="float32 or bfloat16"):
+        with torch.autocast("cuda", dtype=torch.float16):
+            m.float()(torch.randn(1, 9, 64, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MultiHeadLatentAttention(embed_dim=64, num_heads=2)(torch.randn(1, 9, 64))
+    # attention-probability dropout must refuse CUDA-graph capture (its seed is a host value)
+    m = MultiHeadLatentAttention(embed_dim=64, num_heads=2, dropout=0.2).cuda().train()
+    x = torch.randn(2, 9, 64, device="cuda")
+    m(x)
+    g = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="CUDA graph"):
+        with torch.cuda.graph(g):
+            m(x)

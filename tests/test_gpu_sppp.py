@@ -210,3 +210,28 @@ def test_centroids_match_reference_loop(B, H, W, K):
     got = ops.sppp_centroids(torch.from_numpy(lm).cuda(), K)
     assert got.dtype == torch.float32 and got.shape == (B, K, 2)
     assert np.abs(got.cpu().numpy() - ref).max() < 1e-6
+
+
+def test_pool_follows_a_dict_edited_after_map_patches():
+    """The reference API hands out a plain dict: callers may drop / merge / grow superpixels before pooling.  The cached
+    device CSR must not survive such an edit (dict mutation, or in-place edits of the lists inside)."""
+    from favit_b200.sppp import PatchToSuperpixelMapper, SuperpixelPooling
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(1, 64, 4, seed=2, device="cuda", exact_k=True, patch_size=8)[0]
+    x = torch.randn(64, 24, device="cuda")
+    mapper, pool = PatchToSuperpixelMapper(8), SuperpixelPooling("mean")
+    ref = lambda d: torch.stack([x[v].mean(dim=0) for v in d.values()])
+    d = mapper.map_patches(lm, 64)
+    assert d.assignment is not None
+    assert torch.allclose(pool.pool(x, d), ref(d), atol=1e-6)
+    k0, k1 = list(d)[:2]
+    d[k0] = d[k0] + d.pop(k1)                       # merge two superpixels: R drops by one
+    assert d.assignment is None
+    out = pool.pool(x, d)
+    assert out.shape == (len(d), 24) and torch.allclose(out, ref(d), atol=1e-6)
+    d2 = mapper.map_patches(lm, 64)
+    d2[k1].pop()                                    # in-place edit of a list: the dict itself does not notice
+    out2 = pool.pool(x, d2)
+    assert torch.allclose(out2, ref(d2), atol=1e-6)
+    with pytest.raises(IndexError):
+        pool.pool(x, {0: [0, 1], 1: [64]})          # patch id out of range: the reference's fancy indexing raises too
