@@ -1,0 +1,103 @@
+// Patch-embedding + superpixel pooling, algebraically fused.
+//
+// /root/reference/models/sppp_mhla.py:281-300 projects every patch (models/vit.py:36-41: einops
+// 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' + Linear) and then averages the embeddings of the patches of each superpixel
+// (models/sppp.py:209-210).  Both steps are linear, so   mean_p (W x_p + b) = W (mean_p x_p) + b :
+// this kernel averages the RAW pixel patches of every superpixel straight out of the image, and the projection then
+// runs on R rows per image instead of P (12x fewer at 224 px / patch 16 / 16 superpixels, 64x at 512 px / patch 8 / 64).
+// The [B, P, D] embedding tensor, its pooling backward and the P-row weight-gradient GEMM never exist.
+//
+// One CTA per (image, slot).  Threads walk the 3 ps^2 features of a pixel patch in MEMORY order (channel, row, column:
+// ps consecutive floats = 64 bytes at ps 16, whole 32-byte sectors at ps 8) and add the slot's patches in ascending
+// patch order — the CSR of favit_sppp_assign — so the result is deterministic; the feature vector is transposed to the
+// Linear's (p1 p2 c) order in shared memory and stored coalesced.  HBM-bound: every image byte is read exactly once.
+#include "favit_common.cuh"
+
+namespace favit {
+namespace {
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) sppp_pool_pixels_kernel(const float* __restrict__ img,
+                                                               const int32_t* __restrict__ order,
+                                                               const int32_t* __restrict__ offsets,
+                                                               const int32_t* __restrict__ num_slots,
+                                                               TOut* __restrict__ out, int C, int img_h, int img_w, int ps,
+                                                               int grid, int P, int R, int r_cap) {
+  extern __shared__ float s_dyn[];
+  const int F = ps * ps * C;
+  float* s_out = s_dyn;                                  // [F] in (p1 p2 c) order
+  int* s_off = reinterpret_cast<int*>(s_dyn + F);        // [patches of this slot] pixel offset of each patch's corner
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const int ns = min(min(num_slots[b], r_cap), R);
+  const int beg = r < ns ? offsets[(int64_t)b * (r_cap + 1) + r] : 0;
+  const int end = r < ns ? offsets[(int64_t)b * (r_cap + 1) + r + 1] : 0;
+  const int n = end - beg;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int p = order[(int64_t)b * P + beg + t];
+    const int i = p / grid, j = p - i * grid;
+    s_off[t] = i * ps * img_w + j * ps;
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)max(n, 1);
+  const int pp = ps * ps;
+  for (int e = threadIdx.x; e < F; e += blockDim.x) {
+    const int c = e / pp, rem = e - c * pp;
+    const int p1 = rem / ps, p2 = rem - p1 * ps;
+    const float* base = img + ((int64_t)(b * C + c) * img_h + p1) * img_w + p2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains: loads in flight, fixed summation order
+    int t = 0;
+    for (; t + 4 <= n; t += 4) {
+      a0 += __ldg(base + s_off[t]);
+      a1 += __ldg(base + s_off[t + 1]);
+      a2 += __ldg(base + s_off[t + 2]);
+      a3 += __ldg(base + s_off[t + 3]);
+    }
+    for (; t < n; ++t) a0 += __ldg(base + s_off[t]);
+    s_out[(p1 * ps + p2) * C + c] = ((a0 + a1) + (a2 + a3)) * inv;
+  }
+  __syncthreads();
+  TOut* o = out + (int64_t)blockIdx.x * F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) Elem<TOut>::st(o + f, s_out[f]);
+}
+
+}  // namespace
+}  // namespace favit
+
+using namespace favit;
+
+extern "C" int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_w, int patch, int grid,
+                                      const int32_t* order, const int32_t* offsets, const int32_t* num_slots, void* out,
+                                      favit_dtype out_dtype, int R, int r_cap, favit_stream stream) {
+  FAVIT_CHECK_ARG(image && order && offsets && num_slots && out, "sppp_pool_pixels: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && C > 0 && patch > 0 && grid > 0 && R > 0 && r_cap > 0, "sppp_pool_pixels: sizes must be > 0");
+  FAVIT_CHECK_ARG((int64_t)grid * patch <= img_h && (int64_t)grid * patch <= img_w,
+                  "sppp_pool_pixels: grid*patch (%d) exceeds the image (%dx%d)", grid * patch, img_h, img_w);
+  FAVIT_CHECK_ARG((int64_t)B * R < INT32_MAX && (int64_t)B * C * img_h * img_w < ((int64_t)1 << 40),
+                  "sppp_pool_pixels: problem too large");
+  const int P = grid * grid;
+  const size_t smem = ((size_t)patch * patch * C + (size_t)P) * 4;
+  if (smem > 200 * 1024) {
+    set_error("sppp_pool_pixels: %zu bytes of shared memory per CTA (patch %d, %d channels, %d patches) unsupported", smem,
+              patch, C, P);
+    return FAVIT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<__nv_bfloat16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  note_kernel("sppp_pool_pixels_kernel grid=%d", B * R);
+  if (out_dtype == FAVIT_BF16)
+    sppp_pool_pixels_kernel<__nv_bfloat16><<<(unsigned)(B * R), 256, smem, st>>>(
+        image, order, offsets, num_slots, (__nv_bfloat16*)out, C, img_h, img_w, patch, grid, P, R, r_cap);
+  else if (out_dtype == FAVIT_F32)
+    sppp_pool_pixels_kernel<float><<<(unsigned)(B * R), 256, smem, st>>>(image, order, offsets, num_slots, (float*)out, C,
+                                                                        img_h, img_w, patch, grid, P, R, r_cap);
+  else { set_error("sppp_pool_pixels: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}

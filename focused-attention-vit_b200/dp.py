@@ -4,21 +4,85 @@ The reference is single-process (no DDP); this is new work.  Para
 registration order (the order backward produces their gradients), into buckets of ~`bucket_mb`.  Gradients stay where
 autograd puts them (`p.grad` is dropped to None every step, so AccumulateGrad adopts the tensor the backward kernel wrote:
 no zero-fill, no `+=` pass, no gather copy); a post-accumulate-grad hook counts a bucket's gradients down and, when the
-bucket is complete, launches ONE coalesced all-reduce(AVG) over its tensors (a single NCCL group, i.e. one NCCL kernel for
-the whole bucket) on NCCL's own stream, ordered after the backward kernels that produced the bucket, while the rest of
-backward keeps running on the compute stream.  `finish()` makes the compute stream wait for the outstanding reductions
-before the optimizer reads the gradients.  All of it is stream-ordered, so it can be captured into the CUDA graph of the
-training step (engine.TrainStep): the collectives then sit in the graph as nodes forked off the backward chain.
+bucket is complete, launches ONE grouped all-reduce(AVG) over its tensors (ncclGroupStart .. ncclGroupEnd: a single NCCL
+kernel for the whole bucket) on a side stream, ordered after the backward kernels that produced the bucket, while the
+rest of backward keeps running on the compute stream.  `finish()` makes the compute stream wait for the outstanding
+reductions before the optimizer reads the gradients.
+
+On CUDA the collectives go through `NcclComm`: a communicator of our own (bootstrapped over the torch.distributed group,
+which stays the plumbing: rendezvous, barriers, the bench's max-over-ranks), driven by direct `ncclAllReduce` calls on a
+stream we own.  Everything is stream-ordered and no other thread touches the events, so the whole exchange can be
+captured into the CUDA graph of the training step (engine.TrainStep): the collectives then sit in the graph as nodes
+forked off the backward chain.  (ProcessGroupNCCL's watchdog / flight recorder query the events of captured collectives
+from another thread, which is what makes capturing torch's own all-reduce fragile.)  With the gloo backend (CPU tests)
+the same buckets go through the process group's `allreduce_coalesced`.
 
 Every op on the path is per image (no BatchNorm, no cross-sample statistic), so averaged gradients of B/N-image shards
 equal the gradient of the B-image batch with a mean loss.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
+
+_NCCL_FLOAT32, _NCCL_AVG, _NCCL_SUM = 7, 4, 0
+
+
+class _UniqueId(C.Structure):
+    _fields_ = [("internal", C.c_byte * 128)]
+
+
+class NcclComm:
+    """A NCCL communicator over the ranks of a torch.distributed group (libnccl.so.2, the copy torch has loaded)."""
+
+    def __init__(self, process_group=None):
+        self.lib = C.CDLL("libnccl.so.2")
+        self.lib.ncclGetErrorString.restype = C.c_char_p
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _UniqueId, C.c_int]
+        self.lib.ncclAllReduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+        self.rank = dist.get_rank(process_group)
+        self.world = dist.get_world_size(process_group)
+        uid = _UniqueId()
+        if self.rank == 0:
+            self._check(self.lib.ncclGetUniqueId(C.byref(uid)), "ncclGetUniqueId")
+        box = [bytes(uid.internal) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        C.memmove(C.byref(uid), box[0], 128)
+        self.comm = C.c_void_p()
+        self._check(self.lib.ncclCommInitRank(C.byref(self.comm), self.world, uid, self.rank), "ncclCommInitRank")
+        self.stream = torch.cuda.Stream()
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {self.lib.ncclGetErrorString(rc).decode(errors='replace')}")
+
+    def all_reduce_avg(self, tensors: List[torch.Tensor]) -> torch.cuda.Event:
+        """In-place average of every tensor over the ranks, as ONE grouped launch on the communicator's stream, ordered
+        after everything enqueued so far on the current stream.  Returns the event that marks its completion; the
+        caller keeps the tensors alive until it has waited for it (they are the parameters' .grad)."""
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        st = C.c_void_p(self.stream.cuda_stream)
+        self._check(self.lib.ncclGroupStart(), "ncclGroupStart")
+        for t in tensors:
+            if not t.is_contiguous() or t.dtype != torch.float32:
+                raise TypeError("NcclComm.all_reduce_avg takes contiguous fp32 tensors")
+            p = C.c_void_p(t.data_ptr())
+            self._check(self.lib.ncclAllReduce(p, p, t.numel(), _NCCL_FLOAT32, _NCCL_AVG, self.comm, st), "ncclAllReduce")
+        self._check(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def destroy(self) -> None:
+        if self.comm:
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = C.c_void_p()
 
 
 class GradAllReducer:
@@ -35,8 +99,9 @@ class GradAllReducer:
         self._pending: List[int] = []
         self._works = []
         self._handles = []
-        self.overlap = True          # False: hooks are silent and finish() reduces everything in one coalesced call
-        self.collectives = 0         # all-reduce calls issued since construction (bench.py reports it per step)
+        self.overlap = True          # False: hooks are silent and finish() reduces everything in one grouped call
+        self.collectives = 0         # all-reduce launches issued since construction
+        self.nccl: Optional[NcclComm] = None
         if not self.enabled:
             return
         for p in self.params:
@@ -57,9 +122,10 @@ class GradAllReducer:
             for p in b:
                 self._bucket_of[p] = bi
         self._pending = [len(b) for b in self.buckets]
-        self._pg = process_group if process_group is not None else dist.distributed_c10d._get_default_group()
-        # gloo has no AVG: sum and scale afterwards
-        self._avg = dist.get_backend(process_group) == "nccl"
+        if dist.get_backend(process_group) == "nccl" and self.params and self.params[0].is_cuda:
+            self.nccl = NcclComm(process_group)
+        else:
+            self._pg = process_group if process_group is not None else dist.distributed_c10d._get_default_group()
         for p in self.params:
             self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
 
@@ -74,9 +140,11 @@ class GradAllReducer:
             self._works = []
 
     def _reduce(self, tensors: List[torch.Tensor]):
-        opts = dist.AllreduceCoalescedOptions()
-        opts.reduceOp = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self.collectives += 1
+        if self.nccl is not None:
+            return self.nccl.all_reduce_avg(tensors), tensors
+        opts = dist.AllreduceCoalescedOptions()
+        opts.reduceOp = dist.ReduceOp.SUM          # gloo has no AVG: sum and scale afterwards
         return self._pg.allreduce_coalesced(tensors, opts), tensors
 
     def _hook(self, p: torch.nn.Parameter) -> None:
@@ -88,7 +156,7 @@ class GradAllReducer:
             self._works.append(self._reduce([q.grad for q in self.buckets[bi]]))
 
     def finish(self) -> None:
-        """Reduce what the hooks have not (deferred mode: everything, in one coalesced call; overlapped mode: buckets
+        """Reduce what the hooks have not (deferred mode: everything, in one grouped call; overlapped mode: buckets
         with parameters that got no gradient this step), then wait — stream-wise on CUDA — for every outstanding
         reduction.  Parameters without a gradient are skipped; they must be the same on every rank."""
         if not self.enabled:
@@ -105,8 +173,10 @@ class GradAllReducer:
                         self._works.append(self._reduce(left))
         self._pending = [0] * len(self._pending)
         for w, tensors in self._works:
-            w.wait()
-            if not self._avg:
+            if self.nccl is not None:
+                torch.cuda.current_stream().wait_event(w)
+            else:
+                w.wait()
                 torch._foreach_div_(tensors, float(self.world))
         self._works = []
 
@@ -114,6 +184,9 @@ class GradAllReducer:
         for h in self._handles:
             h.remove()
         self._handles = []
+        if self.nccl is not None:
+            self.nccl.destroy()
+            self.nccl = None
 
     @property
     def grad_bytes(self) -> int:

@@ -266,6 +266,9 @@ class SPPPViTMHLA(nn.Module):
         self.norm = nn.LayerNorm(embed_dim)
         self.head = nn.Linear(embed_dim, num_classes)
         self.validate_slots = True   # one D2H read per forward; bench.py checks its synthetic maps once up front
+        # 'mean' pooling commutes with the linear patch embedding: pool the raw pixel patches of every superpixel, then
+        # project R rows per image instead of P.  False = the reference's two steps (embed, then pool).
+        self.fuse_patch_pool = True
         self._init_weights()
 
     def _init_weights(self):
@@ -295,14 +298,36 @@ class SPPPViTMHLA(nn.Module):
         cy = torch.where(has, sy / n.clamp_min(1), torch.full_like(sy, 0.5))
         return torch.stack([cx, cy], dim=-1).view(B, K, 2)
 
+    def _pooled_patch_embeddings(self, x: torch.Tensor, assignment) -> torch.Tensor:
+        """patch_embed + pool('mean') of sppp_mhla.py:281-300 as segment-mean of the raw pixel patches (one pass over the
+        image, favit_sppp_pool_pixels) followed by the projection of the R pooled rows (favit GEMM; its autograd gives
+        the Linear's weight / bias gradients).  fp32 out, like the reference's pool (sppp.py:198)."""
+        from . import ops
+        K = self.num_superpixels
+        if self.validate_slots:
+            ns = assignment.num_slots
+            lo, hi = int(ns.min()), int(ns.max())
+            if lo != hi or lo != K:
+                raise RuntimeError(f"stack expects each tensor to be equal size: images have between {lo} and {hi} "
+                                   f"superpixel slots, expected {K} (reference sppp_mhla.py:300)")
+        cd = compute_dtype(x)
+        lin = self.patch_embed.projection[1]
+        px = ops.sppp_pool_pixels(x, assignment.order, assignment.offsets, assignment.num_slots, self.patch_size, K, cd)
+        with torch.autocast("cuda", enabled=False):
+            return ops.linear(px, lin.weight, lin.bias).float()
+
     def forward(self, x: torch.Tensor, segmentation_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
         batch_size = x.shape[0]
         if segmentation_maps is None:
             segmentation_maps = self.segmentation.segment(x)
-        patch_embeddings = self.patch_embed(x)
         assignment = self.patch_mapper.assign_batch(segmentation_maps, self.img_size, r_cap=self.num_superpixels)
-        pooled = self.pooling.pool_batch(patch_embeddings, assignment, self.num_superpixels,
-                                         validate=self.validate_slots)
+        if (self.fuse_patch_pool and self.pooling.pooling_type == 'mean' and x.is_cuda and x.dtype == torch.float32
+                and not x.requires_grad and x.shape[-1] % self.patch_size == 0 and x.shape[-2] % self.patch_size == 0):
+            pooled = self._pooled_patch_embeddings(x, assignment)
+        else:
+            patch_embeddings = self.patch_embed(x)
+            pooled = self.pooling.pool_batch(patch_embeddings, assignment, self.num_superpixels,
+                                             validate=self.validate_slots)
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), pooled), dim=1)
         x = run_blocks(self.blocks, self.pos_embed(x, self._calculate_superpixel_centroids(segmentation_maps)))
         # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone

@@ -371,6 +371,35 @@ def _(x, order, offsets, num_slots, R, out_dtype):
     return x.new_empty((x.shape[0], R, x.shape[2]), dtype=out_dtype)
 
 
+@torch.library.custom_op("favit::sppp_pool_pixels", mutates_args=())
+def sppp_pool_pixels(image: Tensor, order: Tensor, offsets: Tensor, num_slots: Tensor, patch_size: int, R: int,
+                     out_dtype: torch.dtype) -> Tensor:
+    """image fp32 [B,C,H,W] -> [B, R, patch*patch*C]: the mean RAW pixel patch of every superpixel slot, in the feature
+    order of PatchEmbedding's Linear ('p1 p2 c').  Projecting it gives the pooled patch embeddings (sppp_mhla.py:281-300)
+    with R instead of P rows per image.  No gradient flows to the image."""
+    _cuda(image, order, offsets, num_slots)
+    if image.dtype != torch.float32 or image.dim() != 4:
+        raise ValueError("sppp_pool_pixels: image must be an fp32 [B,C,H,W] tensor")
+    image = image.contiguous()
+    B, Cc, Hh, Ww = image.shape
+    g = Hh // patch_size
+    r_cap = offsets.shape[1] - 1
+    F = patch_size * patch_size * Cc
+    out = torch.empty((B, R, F), dtype=out_dtype, device=image.device)
+    if out.numel():
+        work = float(B * Cc * (g * patch_size) ** 2 * 4 + out.numel() * out.element_size() + B * g * g * 4)
+        rc = L.call("sppp_pool_pixels", work, L.lib().favit_sppp_pool_pixels, _p(image), B, Cc, Hh, Ww, patch_size, g,
+                    _p(order), _p(offsets), _p(num_slots), _p(out), _DT[out_dtype], R, r_cap, _stream())
+        L.check(rc, "favit_sppp_pool_pixels")
+    return out
+
+
+@sppp_pool_pixels.register_fake
+def _(image, order, offsets, num_slots, patch_size, R, out_dtype):
+    B, Cc = image.shape[0], image.shape[1]
+    return image.new_empty((B, R, patch_size * patch_size * Cc), dtype=out_dtype)
+
+
 @torch.library.custom_op("favit::sppp_pool_bwd", mutates_args=())
 def sppp_pool_bwd(dout: Tensor, slot: Tensor, counts: Tensor, dx_dtype: torch.dtype) -> Tensor:
     _cuda(dout, slot, counts)

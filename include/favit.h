@@ -247,6 +247,29 @@ int favit_sppp_pool_bwd(const void* dout, favit_dtype dout_dtype, const int32_t*
                         void* dx, favit_dtype dx_dtype, int B, int P, int R, int D, int r_cap,
                         favit_stream stream);
 
+/* Patch embedding + 'mean' pooling fused algebraically — replaces the P-row projection of
+ * models/vit.py:36-41 followed by the per-superpixel mean of models/sppp.py:209-210 (models/sppp_mhla.py:281-300):
+ *   out[b, r, (p1 p2 c)] = mean over the patches p of slot r of image[b, c, i(p)*patch + p1, j(p)*patch + p2]
+ * so that  pooled[b, r, :] = out[b, r, :] . W^T + bias  (mean of a linear map = linear map of the mean): the projection
+ * runs on R rows per image instead of P, and neither the [B,P,D] embeddings nor their gradients exist.
+ * image: fp32 [B, C, img_h, img_w] contiguous (no gradient flows to it); order / offsets / num_slots: the CSR written by
+ * favit_sppp_assign; out: [B, R, patch*patch*C] fp32 or bf16, rows of slots >= num_slots[b] are zero. */
+int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_w, int patch, int grid,
+                           const int32_t* order, const int32_t* offsets, const int32_t* num_slots, void* out,
+                           favit_dtype out_dtype, int R, int r_cap, favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-tensor AdamW — the optimizer.step() of the reference's training loop,
+ * experiments/mhla_pretrained.py:320-327,367 (three parameter groups, latent_proj at 5x lr) / main.py:129-132.
+ * `count` fp32 tensors, HOST arrays of device pointers / sizes / per-tensor lr and weight decay (a parameter group is
+ * just a run of tensors with the same lr / wd); `step` is a DEVICE int64 holding the 1-based step count of this update
+ * (the caller advances it in-stream, so a captured CUDA graph steps correctly); grads are multiplied by grad_scale
+ * first (1/world when the gradient all-reduce sums).  Same update rule as torch.optim.AdamW (decoupled decay).
+ * ---------------------------------------------------------------------------------------------- */
+int favit_adamw_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
+                      void* const* exp_avg_sq, const int64_t* numel, const float* lr, const float* weight_decay,
+                      const int64_t* step, float beta1, float beta2, float eps, float grad_scale, favit_stream stream);
+
 /* The non-default SuperpixelPooling variants (models/sppp.py:178-184, 211-216), same CSR inputs as the mean pool.
  * 'max'      : out[b,r,c] = max over the slot's patches; argmax int32 [B,R,D] (patch id, -1 for an empty row) is saved
  *              for the backward, which routes dout[b,r,c] to dx[b,argmax,c] (dx is zeroed by the call).

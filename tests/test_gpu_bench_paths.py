@@ -307,7 +307,8 @@ def test_vitb_width_graph_step_matches_oracle():
     ref_loss, ref = _oracle_grads(m, xs[i_last], ys[i_last],
                                   lambda sd: oracle.vit_mhla_forward(xs[i_last].double(), sd, 16, 12, 7))
     assert abs(losses[5] - ref_loss) < 3e-2 * max(1.0, abs(ref_loss)), (losses, ref_loss)
-    assert abs(losses[3] - losses[5]) < 1e-6 and abs(losses[1] - losses[5]) < 1e-3    # replay == replay ~= eager, same batch
+    # replay ~= replay ~= eager on the same batch (the folded proj bias is summed with fp32 atomics: last-bit order effects)
+    assert abs(losses[3] - losses[5]) < 1e-4 and abs(losses[1] - losses[5]) < 1e-3
     scale = max(float(r.abs().max()) for r in ref.values())
     for k, p in m.named_parameters():
         assert p.grad is not None, k
@@ -333,7 +334,7 @@ def test_sppp_vits_width_graph_step_matches_oracle():
     maps = voronoi_label_maps(B, 224, K, seed=8, device="cuda", exact_k=True, patch_size=16)
     step = TrainStep(m, lr=0.0, weight_decay=0.0, cuda_graph=True)
     losses = [float(step(x, y, maps)) for _ in range(5)]
-    assert step._graph is not None and abs(losses[-1] - losses[-2]) < 1e-6
+    assert step._graph is not None and abs(losses[-1] - losses[-2]) < 1e-4
     # (1) graph replay of the full batch == eager step of the full batch (same kernels, same inputs).  After a replay
     # the parameters' .grad are the graph's own tensors; the eager step below replaces them with fresh ones.
     grads_graph = {k: p.grad.clone() for k, p in m.named_parameters()}

@@ -235,3 +235,54 @@ def test_pool_follows_a_dict_edited_after_map_patches():
     assert torch.allclose(out2, ref(d2), atol=1e-6)
     with pytest.raises(IndexError):
         pool.pool(x, {0: [0, 1], 1: [64]})          # patch id out of range: the reference's fancy indexing raises too
+
+
+@pytest.mark.parametrize("B,S,ps,K,C", [(3, 32, 4, 4, 3), (4, 224, 16, 16, 3), (2, 512, 8, 64, 3), (2, 64, 8, 16, 1),
+                                        (256, 224, 16, 16, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_pool_pixels_is_patchify_then_segment_mean(B, S, ps, K, C, dtype):
+    """favit_sppp_pool_pixels against the reference's two steps on raw pixels: the einops rearrangement of
+    models/vit.py:38-39 followed by the per-superpixel mean of models/sppp.py:209-210 (fp64)."""
+    from favit_b200 import ops
+    from favit_b200.sppp import PatchToSuperpixelMapper
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(B, S, K, seed=31, device="cuda", exact_k=True, patch_size=ps)
+    a = PatchToSuperpixelMapper(ps).assign_batch(lm, S, r_cap=K)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    img = torch.randn(B, C, S, S, device="cuda", generator=g)
+    out = ops.sppp_pool_pixels(img, a.order, a.offsets, a.num_slots, ps, K, dtype)
+    gs = S // ps
+    patches = img.double().reshape(B, C, gs, ps, gs, ps).permute(0, 2, 4, 3, 5, 1).reshape(B, gs * gs, ps * ps * C)
+    F = ps * ps * C
+    ref = torch.zeros(B, K, F, device="cuda", dtype=torch.float64)
+    ref.scatter_add_(1, a.slot.long()[:, :, None].expand(-1, -1, F), patches)
+    ref /= a.counts.double()[:, :, None]
+    assert out.dtype == dtype and out.shape == (B, K, F)
+    assert rel_err(out, ref) < (2e-6 if dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fused_patch_pool_model_path_equals_two_step_path(mode):
+    """SPPPViTMHLA with the algebraic fusion (pool pixels, project R rows) against the same model with the reference's
+    two steps (project P rows, pool): logits and every gradient, incl. the patch-embedding weight and bias."""
+    from favit_b200.models import SPPPViTMHLA
+    from favit_b200.synth import voronoi_label_maps
+    torch.manual_seed(2)
+    m = SPPPViTMHLA(img_size=64, patch_size=8, num_classes=7, embed_dim=128, depth=2, num_heads=2, num_superpixels=16,
+                    window_size=7, use_mhla=True).cuda()
+    x = torch.randn(6, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 7, (6,), device="cuda")
+    maps = voronoi_label_maps(6, 64, 16, seed=5, device="cuda", exact_k=True, patch_size=8)
+    res = {}
+    for fused in (True, False):
+        m.fuse_patch_pool = fused
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            logits = m(x, maps)
+        torch.nn.functional.cross_entropy(logits.float(), y).backward()
+        res[fused] = (logits.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    tol = 1e-4 if mode == "fp32" else 3e-2
+    assert rel_err(res[True][0], res[False][0]) < tol
+    scale = max(float(v.abs().max()) for v in res[False][1].values())
+    for k in res[False][1]:
+        assert rel_err(res[True][1][k], res[False][1][k], floor=1e-2 * scale) < 3 * tol, k
