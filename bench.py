@@ -587,7 +587,7 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": world * B, "per_gpu_batch": B, "img": wl["img"],
                    "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"], "window": wl["W"],
-                   "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "adamw(fused) in step", "cuda_graph": bool(args.cuda_graph),
+                   "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "favit multi-tensor AdamW kernel, in step", "cuda_graph": bool(args.cuda_graph),
                    "dp_mode": (args.dp_mode + (" (NCCL all-reduce nodes inside the step graph)" if args.cuda_graph and
                                                args.dp_mode != "split" else "")) if dist_on else None,
                    "grad_allreduce_calls_per_step": (len(step.reducer.buckets) if args.dp_mode == "overlap" else 1)

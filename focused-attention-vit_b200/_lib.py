@@ -44,6 +44,7 @@ _SIGS = {
     "favit_layernorm_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp], _i),
     "favit_layernorm_bwd": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "favit_sppp_assign": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "favit_sppp_assign_centroids": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "favit_sppp_centroids": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "favit_sppp_pool_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_max_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),

@@ -288,10 +288,16 @@ __global__ void __launch_bounds__(256) sppp_pool_bwd_kernel(const TIn* __restric
 // 16-byte pairs (needs an even image width and a 16-byte aligned map).  A patch covered by one label (the
 // common case inside a superpixel) costs one vote.  Otherwise labels are counted one distinct value per round,
 // candidates taken in whatever order lanes hold them, ties resolved towards the smaller id (sppp.py:117-120).
-template <int PS>
+// CENT: the same pass also accumulates, per image and label in [0, K), the pixel count and the sums of the x and y
+// coordinates (models/sppp_mhla.py:226-262, the centroids of the dynamic positional encoding) into acc [B][3][K]
+// (64-bit integers, exact and order independent) — the label map is then read ONCE per forward instead of twice.
+// Only when the patches tile the whole image (img_h == img_w == grid * PS); the vote loop then runs until every
+// pixel of a mixed patch has been counted instead of stopping as soon as the winner is known.
+template <int PS, bool CENT>
 __global__ void __launch_bounds__(256) sppp_dominant_vec_kernel(const int64_t* __restrict__ labels,
                                                                 int64_t* __restrict__ dom, int B, int img_h,
-                                                                int img_w, int grid) {
+                                                                int img_w, int grid, unsigned long long* __restrict__ acc,
+                                                                int K) {
   constexpr int NV = PS * PS / 32;             // labels per lane
   constexpr int NP = NV / 2;                   // 16-byte pairs per lane
   constexpr int PAIRS_PER_ROW = PS / 2;        // lanes covering one patch row
@@ -317,27 +323,50 @@ __global__ void __launch_bounds__(256) sppp_dominant_vec_kernel(const int64_t* _
 #pragma unroll
   for (int t = 0; t < NV; ++t) differs |= vals[t] != v0;
   if (!__any_sync(0xffffffffu, differs)) {
-    if (lane == 0) dom[warp] = v0;
+    if (lane == 0) {
+      dom[warp] = v0;
+      if (CENT && v0 >= 0 && v0 < K) {
+        unsigned long long* a = acc + (int64_t)b * 3 * K + v0;
+        atomicAdd(a, (unsigned long long)(PS * PS));
+        atomicAdd(a + K, (unsigned long long)(PS * (PS * pj * PS + PS * (PS - 1) / 2)));
+        atomicAdd(a + 2 * K, (unsigned long long)(PS * (PS * pi * PS + PS * (PS - 1) / 2)));
+      }
+    }
     return;
   }
   unsigned alive = NV == 32 ? 0xffffffffu : ((1u << NV) - 1u);
   int remaining = PS * PS, best_cnt = 0;
   long long best_label = 0;
-  while (remaining > 0 && remaining >= best_cnt) {
+  const int x_lane = pj * PS + 2 * (lane % PAIRS_PER_ROW), y_lane = pi * PS + lane / PAIRS_PER_ROW;
+  while (remaining > 0 && (CENT || remaining >= best_cnt)) {
     const unsigned has = __ballot_sync(0xffffffffu, alive != 0u);
     long long mine = 0;
 #pragma unroll
     for (int t = NV - 1; t >= 0; --t)
       if ((alive >> t) & 1u) mine = vals[t];
     const long long cand = __shfl_sync(0xffffffffu, mine, __ffs(has) - 1);
-    int c = 0;
+    int c = 0, sx = 0, sy = 0;
 #pragma unroll
     for (int t = 0; t < NV; ++t)
       if (((alive >> t) & 1u) && vals[t] == cand) {
         ++c;
         alive &= ~(1u << t);
+        if (CENT) {
+          sx += x_lane + (t & 1);
+          sy += y_lane + (t >> 1) * ROWS_PER_LOAD;
+        }
       }
     c = __reduce_add_sync(0xffffffffu, c);
+    if (CENT) {
+      sx = __reduce_add_sync(0xffffffffu, sx);
+      sy = __reduce_add_sync(0xffffffffu, sy);
+      if (lane == 0 && cand >= 0 && cand < K) {
+        unsigned long long* a = acc + (int64_t)b * 3 * K + cand;
+        atomicAdd(a, (unsigned long long)c);
+        atomicAdd(a + K, (unsigned long long)sx);
+        atomicAdd(a + 2 * K, (unsigned long long)sy);
+      }
+    }
     if (c > best_cnt || (c == best_cnt && cand < best_label)) {
       best_cnt = c;
       best_label = cand;
@@ -1280,10 +1309,10 @@ int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts
 
 using namespace favit;
 
-extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
-                                 int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
-                                 int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap,
-                                 favit_stream stream) {
+static int sppp_assign_impl(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
+                            int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
+                            int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap, int K,
+                            unsigned long long* acc, float* centroids, favit_stream stream) {
   FAVIT_CHECK_ARG(labels && dom && slot && num_slots && counts && slot_label && offsets && order,
                   "sppp_assign: null pointer");
   FAVIT_CHECK_ARG(B > 0 && patch > 0 && grid > 0 && r_cap > 0, "sppp_assign: B, patch, grid, r_cap must be > 0");
@@ -1298,12 +1327,23 @@ extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int im
   const int ppl = ceil_div(patch * patch, 32);
   const unsigned blocks = (unsigned)ceil_div64((int64_t)B * P, 8);
   const bool vec = (img_w % 2 == 0) && ((uintptr_t)labels % 16 == 0);
-  if (vec && patch == 16) {
-    sppp_dominant_vec_kernel<16><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+  // centroids in the same pass: the patches must tile the whole image, and the coordinate sums of a warp stay in int32
+  const bool cent = acc && centroids && vec && (patch == 8 || patch == 16 || patch == 32) && img_h == grid * patch &&
+                    img_w == grid * patch && img_w <= 32768 && img_h <= 32768 && K > 0 && K <= 4096;
+  bool cent_done = false;
+  if (cent) {
+    FAVIT_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * 3 * K * sizeof(unsigned long long), st));
+    if (patch == 16) sppp_dominant_vec_kernel<16, true><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, acc, K);
+    else if (patch == 8) sppp_dominant_vec_kernel<8, true><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, acc, K);
+    else sppp_dominant_vec_kernel<32, true><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, acc, K);
+    cent_done = true;
+    note_kernel("sppp_dominant_vec_kernel<%d, centroids=1>", patch);
+  } else if (vec && patch == 16) {
+    sppp_dominant_vec_kernel<16, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else if (vec && patch == 8) {
-    sppp_dominant_vec_kernel<8><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+    sppp_dominant_vec_kernel<8, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else if (vec && patch == 32) {
-    sppp_dominant_vec_kernel<32><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid);
+    sppp_dominant_vec_kernel<32, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else {
 #define FAVIT_DOM(PPL)                                                                                   \
   sppp_dominant_kernel<PPL><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, patch, grid)
@@ -1333,7 +1373,29 @@ extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int im
     sppp_slot_kernel<1024><<<B, 1024, 0, st>>>(dom, slot, num_slots, counts, slot_label, offsets, order, P, r_cap);
   }
   FAVIT_CHECK_LAUNCH();
+  if (acc && centroids) {
+    if (!cent_done) return favit_sppp_centroids(labels, B, img_h, img_w, K, acc, centroids, stream);  // separate pass
+    sppp_centroid_fin_kernel<<<(unsigned)ceil_div(B * K, 256), 256, 0, st>>>(acc, B, K, img_h, img_w, centroids);
+    FAVIT_CHECK_LAUNCH();
+  }
   return FAVIT_OK;
+}
+
+extern "C" int favit_sppp_assign(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
+                                 int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
+                                 int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap,
+                                 favit_stream stream) {
+  return sppp_assign_impl(labels, B, img_h, img_w, patch, grid, dom, slot, num_slots, counts, slot_label, offsets, order,
+                          r_cap, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int favit_sppp_assign_centroids(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
+                                           int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
+                                           int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap, int K,
+                                           unsigned long long* acc, float* centroids, favit_stream stream) {
+  FAVIT_CHECK_ARG(acc && centroids && K > 0, "sppp_assign_centroids: null accumulator / output or K <= 0");
+  return sppp_assign_impl(labels, B, img_h, img_w, patch, grid, dom, slot, num_slots, counts, slot_label, offsets, order,
+                          r_cap, K, acc, centroids, stream);
 }
 
 extern "C" int favit_sppp_centroids(const int64_t* labels, int B, int img_h, int img_w, int K, unsigned long long* acc,

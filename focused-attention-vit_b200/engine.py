@@ -23,7 +23,7 @@ class TrainStep:
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.05,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 32.0,
-                 optimizer: bool = True, cuda_graph: bool = False, dp_mode: str = "overlap"):
+                 optimizer=True, cuda_graph: bool = False, dp_mode: str = "overlap", param_groups=None):
         """dp_mode (data parallel only): "overlap" = one coalesced all-reduce per gradient bucket, launched from the
         backward hooks and running beside the rest of backward (also inside the captured graph); "deferred" = one
         coalesced all-reduce of every gradient after backward (inside the graph when cuda_graph); "split" = deferred, with
@@ -35,10 +35,19 @@ class TrainStep:
         self.autocast_dtype = autocast_dtype
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group)
         self.reducer.overlap = dp_mode == "overlap"
-        # lr / weight decay: the reference's defaults (main.py:129-132)
-        self.opt = (torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
-                                      capturable=cuda_graph)
-                    if optimizer else None)
+        # lr / weight decay: the reference's defaults (main.py:129-132).  optimizer: True / "favit" = the multi-tensor
+        # AdamW kernel of this library (optim.FusedAdamW; `param_groups` = e.g. optim.reference_param_groups for the three
+        # groups of experiments/mhla_pretrained.py:320-327), "torch" = torch.optim.AdamW(fused=True), False = none
+        groups = param_groups if param_groups is not None else model.parameters()
+        if optimizer in (True, "favit"):
+            from .optim import FusedAdamW
+            self.opt = FusedAdamW(groups, lr=lr, weight_decay=weight_decay)
+        elif optimizer == "torch":
+            self.opt = torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=True, capturable=cuda_graph)
+        elif not optimizer:
+            self.opt = None
+        else:
+            raise ValueError(f"unknown optimizer {optimizer!r}")
         self.cuda_graph = cuda_graph
         self._graph = None
         self._graph_opt = None

@@ -320,7 +320,13 @@ class SPPPViTMHLA(nn.Module):
         batch_size = x.shape[0]
         if segmentation_maps is None:
             segmentation_maps = self.segmentation.segment(x)
-        assignment = self.patch_mapper.assign_batch(segmentation_maps, self.img_size, r_cap=self.num_superpixels)
+        centroids = None
+        if segmentation_maps.is_cuda and segmentation_maps.dim() == 3 and self.num_superpixels <= 4096:
+            # dominant labels and centroids from one pass over the label maps
+            assignment, centroids = self.patch_mapper.assign_batch_with_centroids(
+                segmentation_maps, self.img_size, self.num_superpixels, self.num_superpixels)
+        else:
+            assignment = self.patch_mapper.assign_batch(segmentation_maps, self.img_size, r_cap=self.num_superpixels)
         if (self.fuse_patch_pool and self.pooling.pooling_type == 'mean' and x.is_cuda and x.dtype == torch.float32
                 and not x.requires_grad and x.shape[-1] % self.patch_size == 0 and x.shape[-2] % self.patch_size == 0):
             pooled = self._pooled_patch_embeddings(x, assignment)
@@ -329,7 +335,9 @@ class SPPPViTMHLA(nn.Module):
             pooled = self.pooling.pool_batch(patch_embeddings, assignment, self.num_superpixels,
                                              validate=self.validate_slots)
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), pooled), dim=1)
-        x = run_blocks(self.blocks, self.pos_embed(x, self._calculate_superpixel_centroids(segmentation_maps)))
+        if centroids is None:
+            centroids = self._calculate_superpixel_centroids(segmentation_maps)
+        x = run_blocks(self.blocks, self.pos_embed(x, centroids))
         # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone
         return self.head(self.norm(x[:, 0]))
 

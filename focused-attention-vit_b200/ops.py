@@ -327,6 +327,47 @@ def _(labels, patch_size, img_size, r_cap):
             labels.new_empty((B, P), dtype=i32)]
 
 
+@torch.library.custom_op("favit::sppp_assign_centroids", mutates_args=())
+def sppp_assign_centroids(labels: Tensor, patch_size: int, img_size: int, r_cap: int, K: int) -> List[Tensor]:
+    """sppp_assign + sppp_centroids with a single pass over the label map: the seven tensors of sppp_assign followed by
+    the fp32 [B,K,2] centroids."""
+    _cuda(labels)
+    if labels.dtype != torch.int64 or labels.dim() != 3:
+        raise ValueError("sppp_assign_centroids: labels must be an int64 [B,H,W] tensor")
+    labels = labels.contiguous()
+    B, Hh, Ww = labels.shape
+    g = img_size // patch_size
+    P = g * g
+    dev = labels.device
+    dom = torch.empty((B, P), dtype=torch.int64, device=dev)
+    slot = torch.empty((B, P), dtype=torch.int32, device=dev)
+    num_slots = torch.empty((B,), dtype=torch.int32, device=dev)
+    counts = torch.empty((B, r_cap), dtype=torch.int32, device=dev)
+    slot_label = torch.empty((B, r_cap), dtype=torch.int64, device=dev)
+    offsets = torch.empty((B, r_cap + 1), dtype=torch.int32, device=dev)
+    order = torch.empty((B, P), dtype=torch.int32, device=dev)
+    cent = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    if B * P and K:
+        acc = torch.empty((B, 3, K), dtype=torch.int64, device=dev)
+        work = B * Hh * Ww * 8.0 + 2.0 * B * P * 4 + B * r_cap * 4 + B * K * 8.0
+        rc = L.call("sppp_assign", work, L.lib().favit_sppp_assign_centroids, _p(labels), B, Hh, Ww, patch_size, g, _p(dom),
+                    _p(slot), _p(num_slots), _p(counts), _p(slot_label), _p(offsets), _p(order), r_cap, K, _p(acc),
+                    _p(cent), _stream())
+        L.check(rc, "favit_sppp_assign_centroids")
+    return [dom, slot, num_slots, counts, slot_label, offsets, order, cent]
+
+
+@sppp_assign_centroids.register_fake
+def _(labels, patch_size, img_size, r_cap, K):
+    B = labels.shape[0]
+    P = (img_size // patch_size) ** 2
+    i32, i64 = torch.int32, torch.int64
+    return [labels.new_empty((B, P), dtype=i64), labels.new_empty((B, P), dtype=i32),
+            labels.new_empty((B,), dtype=i32), labels.new_empty((B, r_cap), dtype=i32),
+            labels.new_empty((B, r_cap), dtype=i64), labels.new_empty((B, r_cap + 1), dtype=i32),
+            labels.new_empty((B, P), dtype=i32), labels.new_empty((B, K, 2), dtype=torch.float32)]
+
+
 @torch.library.custom_op("favit::sppp_centroids", mutates_args=())
 def sppp_centroids(labels: Tensor, K: int) -> Tensor:
     """labels int64 [B,H,W] -> fp32 [B,K,2] (x, y) centroids of labels 0..K-1 in normalised coordinates, (0.5, 0.5) for

@@ -75,3 +75,14 @@ class FusedAdamW(torch.optim.Optimizer):
                         self._step_t.data_ptr(), b1, b2, eps, float(self.grad_scale), stream)
             L.check(rc, "favit_adamw_multi")
         return loss
+
+
+def reference_param_groups(model: torch.nn.Module, lr: float, head_lr: float, latent_lr_mult: float = 5.0):
+    """The three AdamW parameter groups of the reference's training loop (experiments/mhla_pretrained.py:320-327):
+    everything but the head and the latent projections at `lr`, `latent_proj` at 5 x lr, the head at `head_lr`."""
+    named = list(model.named_parameters())
+    return [
+        {"params": [p for n, p in named if "head" not in n and "latent_proj" not in n], "lr": lr},
+        {"params": [p for n, p in named if "latent_proj" in n], "lr": lr * latent_lr_mult},
+        {"params": list(model.head.parameters()), "lr": head_lr},
+    ]

@@ -104,6 +104,15 @@ class PatchToSuperpixelMapper:
         dom, slot, num_slots, counts, slot_label, offsets, order = ops.sppp_assign(seg, self.patch_size, img_size, cap)
         return SuperpixelAssignment(dom, slot, num_slots, counts, slot_label, offsets, order, cap)
 
+    def assign_batch_with_centroids(self, segmentation_maps: torch.Tensor, img_size: int, r_cap: int, num_superpixels: int):
+        """(SuperpixelAssignment, centroids fp32 [B,K,2]) from ONE pass over the label maps: `assign_batch` plus the
+        superpixel centroids of models/sppp_mhla.py:226-262."""
+        seg = segmentation_maps
+        if seg.dtype != torch.int64:
+            seg = seg.to(torch.int64)
+        *a, cent = ops.sppp_assign_centroids(seg, self.patch_size, img_size, r_cap, num_superpixels)
+        return SuperpixelAssignment(*a, r_cap), cent
+
     def map_patches(self, segmentation_map: torch.Tensor, img_size: int) -> Dict[int, List[int]]:
         """One image [H,W] -> {dominant label: [patch indices]} in first-seen order (sppp.py:91-128)."""
         a = self.assign_batch(segmentation_map.unsqueeze(0), img_size)

@@ -235,6 +235,15 @@ int favit_sppp_assign(const int64_t* labels, int B, int img_h, int img_w, int pa
 int favit_sppp_centroids(const int64_t* labels, int B, int img_h, int img_w, int K, unsigned long long* acc,
                          float* centroids, favit_stream stream);
 
+/* favit_sppp_assign and favit_sppp_centroids in ONE pass over the label map (the largest tensor of the SPPP front end:
+ * 103 MB per 256-image batch at 224 px): the dominant-label kernel also accumulates the per-label pixel counts and
+ * coordinate sums.  Used when the patches tile the whole image (img_h == img_w == grid * patch, patch 8 / 16 / 32);
+ * otherwise the two kernels run one after the other.  Outputs as in the two separate calls. */
+int favit_sppp_assign_centroids(const int64_t* labels, int B, int img_h, int img_w, int patch, int grid,
+                                int64_t* dom, int32_t* slot, int32_t* num_slots, int32_t* counts,
+                                int64_t* slot_label, int32_t* offsets, int32_t* order, int r_cap, int K,
+                                unsigned long long* acc, float* centroids, favit_stream stream);
+
 /* SuperpixelPooling.pool('mean') — replaces models/sppp.py:192-223 + the per-image loop/stack at
  * models/sppp_mhla.py:286-300.  x[B,P,D] (x_dtype) -> out[B,R,D] (out_dtype; the reference always
  * produces fp32, sppp.py:198).  Rows r >= num_slots[b] are zero-filled. */

@@ -286,3 +286,29 @@ def test_fused_patch_pool_model_path_equals_two_step_path(mode):
     scale = max(float(v.abs().max()) for v in res[False][1].values())
     for k in res[False][1]:
         assert rel_err(res[True][1][k], res[False][1][k], floor=1e-2 * scale) < 3 * tol, k
+
+
+@pytest.mark.parametrize("B,S,ps,K", [(5, 224, 16, 16), (3, 512, 8, 64), (2, 96, 32, 9), (3, 64, 8, 4), (2, 100, 8, 9),
+                                      (2, 224, 14, 16), (256, 224, 16, 16)])
+def test_assign_with_centroids_in_one_pass_equals_the_two_kernels(B, S, ps, K):
+    """favit_sppp_assign_centroids (dominant labels + centroid sums from ONE pass over the label map) against the two
+    separate entry points: every integer output identical, centroids identical (both are exact integer sums divided
+    once), for tiling patch sizes (fused pass), a ragged image (100 % 8 != 0) and patch 14 (separate passes), and with
+    labels outside [0, K) and absent labels."""
+    from favit_b200 import _lib as L, ops
+    from favit_b200.synth import voronoi_label_maps
+    lm = voronoi_label_maps(B, S, K, seed=S + K, device="cuda")
+    lm[0][lm[0] == 1] = K + 5            # a label >= K: dominates patches, ignored by the centroids; label 1 is now absent
+    lm[B - 1][: S // 3, : S // 2] = -3     # negative labels
+    got = ops.sppp_assign_centroids(lm, ps, S, K, K)
+    fused = "centroids=1" in L.last_kernel()
+    assert fused == (S % ps == 0 and ps in (8, 16, 32)), L.last_kernel()
+    ref = ops.sppp_assign(lm, ps, S, K)
+    for a, b in zip(got[:7], ref):
+        assert torch.equal(a, b)
+    cen = ops.sppp_centroids(lm, K)
+    assert torch.equal(got[7], cen)
+    assert torch.allclose(got[7][0, 1], torch.tensor([0.5, 0.5], device="cuda"))
+    import oracle
+    idx = [0, B - 1]
+    assert torch.allclose(got[7][idx].cpu(), oracle.superpixel_centroids(lm[idx].cpu(), K), atol=1e-5)
