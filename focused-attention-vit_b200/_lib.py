@@ -53,7 +53,7 @@ _SIGS = {
     "favit_sppp_pool_attn_bwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_pixels": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "favit_adamw_multi": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
-                           C.POINTER(_f), C.POINTER(_f), _vp, _f, _f, _f, _f, _vp], _i),
+                           C.POINTER(_f), C.POINTER(_f), _vp, C.c_double, C.c_double, _f, _f, _vp], _i),
     "favit_sppp_pool_bwd": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
 }
 

@@ -25,15 +25,18 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ AdamTable t,
-                                                          const long long* __restrict__ step, float beta1, float beta2,
+                                                          const long long* __restrict__ step, double beta1_d, double beta2_d,
                                                           float eps, float grad_scale) {
   const int ti = blockIdx.y;
   const long long n = t.n[ti];
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  const float s = (float)__ldg(step);
-  const float bc1 = 1.f - powf(beta1, s), bc2 = 1.f - powf(beta2, s);
+  // hyper-parameter arithmetic in double, like the Python side of torch.optim.AdamW: 1 - 0.999f is off by 5e-5 in fp32
+  const double s = (double)__ldg(step);
+  const float bc1 = (float)(1.0 - pow(beta1_d, s)), bc2 = (float)(1.0 - pow(beta2_d, s));
+  const float beta1 = (float)beta1_d, beta2 = (float)beta2_d;
+  const float omb1 = (float)(1.0 - beta1_d), omb2 = (float)(1.0 - beta2_d);
   const float lr = t.lr[ti], decay = 1.f - lr * t.wd[ti];
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   float* __restrict__ p = t.p[ti];
@@ -59,8 +62,8 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant_
     for (int e = 0; e < 4; ++e) {
       const float ge = gg[e] * grad_scale;
       pp[e] *= decay;
-      mm[e] = beta1 * mm[e] + (1.f - beta1) * ge;
-      vv[e] = beta2 * vv[e] + (1.f - beta2) * ge * ge;
+      mm[e] = beta1 * mm[e] + omb1 * ge;
+      vv[e] = beta2 * vv[e] + omb2 * ge * ge;
       const float denom = sqrtf(vv[e]) * inv_sqrt_bc2 + eps;
       pp[e] -= step_size * (mm[e] / denom);
     }
@@ -81,11 +84,11 @@ using namespace favit;
 
 extern "C" int favit_adamw_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
                                  void* const* exp_avg_sq, const int64_t* numel, const float* lr, const float* weight_decay,
-                                 const int64_t* step, float beta1, float beta2, float eps, float grad_scale,
+                                 const int64_t* step, double beta1, double beta2, float eps, float grad_scale,
                                  favit_stream stream) {
   FAVIT_CHECK_ARG(count > 0 && params && grads && exp_avg && exp_avg_sq && numel && lr && weight_decay && step,
                   "adamw_multi: bad argument");
-  FAVIT_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adamw_multi: bad hyper-parameters");
+  FAVIT_CHECK_ARG(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0.f, "adamw_multi: bad hyper-parameters");
   cudaStream_t st = (cudaStream_t)stream;
   for (int t0 = 0; t0 < count; t0 += kAdamMax) {
     const int n = count - t0 < kAdamMax ? count - t0 : kAdamMax;

@@ -1339,12 +1339,16 @@ static int sppp_assign_impl(const int64_t* labels, int B, int img_h, int img_w, 
     cent_done = true;
     note_kernel("sppp_dominant_vec_kernel<%d, centroids=1>", patch);
   } else if (vec && patch == 16) {
+    note_kernel("sppp_dominant_vec_kernel<16, centroids=0>");
     sppp_dominant_vec_kernel<16, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else if (vec && patch == 8) {
+    note_kernel("sppp_dominant_vec_kernel<8, centroids=0>");
     sppp_dominant_vec_kernel<8, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else if (vec && patch == 32) {
+    note_kernel("sppp_dominant_vec_kernel<32, centroids=0>");
     sppp_dominant_vec_kernel<32, false><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, grid, nullptr, 0);
   } else {
+    note_kernel("sppp_dominant_kernel (scalar loads, patch %d)", patch);
 #define FAVIT_DOM(PPL)                                                                                   \
   sppp_dominant_kernel<PPL><<<blocks, 256, 0, st>>>(labels, dom, B, img_h, img_w, patch, grid)
     if (ppl <= 1) FAVIT_DOM(1);

@@ -277,7 +277,7 @@ int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_
  * ---------------------------------------------------------------------------------------------- */
 int favit_adamw_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
                       void* const* exp_avg_sq, const int64_t* numel, const float* lr, const float* weight_decay,
-                      const int64_t* step, float beta1, float beta2, float eps, float grad_scale, favit_stream stream);
+                      const int64_t* step, double beta1, double beta2, float eps, float grad_scale, favit_stream stream);
 
 /* The non-default SuperpixelPooling variants (models/sppp.py:178-184, 211-216), same CSR inputs as the mean pool.
  * 'max'      : out[b,r,c] = max over the slot's patches; argmax int32 [B,R,D] (patch id, -1 for an empty row) is saved

@@ -92,5 +92,10 @@ def test_train_step_with_reference_param_groups():
     for _ in range(3):
         l1, l2 = s1(x, y), s2(x, y)
     assert abs(float(l1) - float(l2)) < 1e-4
+    D = 128
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if k.endswith("attn.qkv.bias"):
+            # the K third of the qkv bias has an analytically zero gradient (a shift of all keys cancels in the softmax):
+            # Adam normalises the rounding noise there into +-lr steps, which no two implementations reproduce
+            p1, p2 = torch.cat([p1[:D], p1[2 * D:]]), torch.cat([p2[:D], p2[2 * D:]])
         assert rel_err(p1, p2) < 1e-4, k
