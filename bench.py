@@ -215,8 +215,12 @@ def timed_steps(fn, steps, dist_on, device):
     e1.record()
     torch.cuda.synchronize(device)
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    timed_steps.by_rank = [float(ms.item())]
     if dist_on:
         dist.barrier()
+        every = [torch.zeros_like(ms) for _ in range(dist.get_world_size())]
+        dist.all_gather(every, ms)
+        timed_steps.by_rank = [float(t.item()) for t in every]      # each rank's own elapsed time (ms, total)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
 
@@ -457,6 +461,7 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     launches0 = L.launch_count()
     sampler.start()
     ms_total = timed_steps(dev_step, args.steps, dist_on, device)
+    ms_by_rank = [round(t / args.steps, 3) for t in timed_steps.by_rank]
     clocks = sampler.stop()
     launches = L.launch_count() - launches0
     prof, L.PROFILE = (L.PROFILE or []), None
@@ -583,7 +588,8 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_per_step_by_rank": ms_by_rank,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": world * B, "per_gpu_batch": B, "img": wl["img"],
                    "patch": wl["ps"], "embed_dim": wl["D"], "depth": wl["depth"], "heads": wl["H"], "window": wl["W"],
@@ -629,7 +635,7 @@ def main():
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true",
                     help="capture the training step in a CUDA graph (default)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
-    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split"],
+    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
                     help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
                          "(default), one collective after backward, or one collective outside the step graph")
     ap.set_defaults(cuda_graph=None)

@@ -1018,6 +1018,69 @@ __global__ void __launch_bounds__(kBwdThreads) sppp_pool_bwd_tile_kernel(const T
   }
 }
 
+// Whole-row variant: one CTA per (image, chunk of consecutive patch rows).  The R gradient rows of the image, already
+// divided by their counts and rounded to the OUTPUT type (so that replicating them is a pure copy and gives the same
+// bits as dividing per patch), sit in shared memory; the CTA then writes its rows x D block of dx — one contiguous
+// range of global memory — 16 bytes per thread, consecutive threads at consecutive addresses.  Column-sliced CTAs
+// (above) write 128-byte pieces D*es bytes apart, which costs DRAM write efficiency: 0.60 of the copy bandwidth at
+// best; contiguous rows stream.
+constexpr int kBwdRowsThreads = 256;
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kBwdRowsThreads) sppp_pool_bwd_rows_kernel(const TIn* __restrict__ dout,
+                                                                             const int32_t* __restrict__ slot,
+                                                                             const int32_t* __restrict__ counts,
+                                                                             TOut* __restrict__ dx, int P, int R, int D,
+                                                                             int r_cap, int nchunks, int rows_per_chunk) {
+  constexpr int NVO = 16 / (int)sizeof(TOut);
+  extern __shared__ __align__(16) unsigned char s_rows_raw[];
+  TOut* s_g = reinterpret_cast<TOut*>(s_rows_raw);                       // [R][D] in the output type
+  int* s_slot = reinterpret_cast<int*>(s_rows_raw + (size_t)R * D * sizeof(TOut));   // [rows_per_chunk]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / nchunks, ch = blockIdx.x - b * nchunks;
+  const int p0 = ch * rows_per_chunk, p1 = min(P, p0 + rows_per_chunk);
+  for (int i = tid; i < p1 - p0; i += kBwdRowsThreads) {
+    const int r = slot[(int64_t)b * P + p0 + i];
+    s_slot[i] = (r >= 0 && r < R && r < r_cap) ? r : -1;
+  }
+  const int cpr = D / NVO;  // 16-byte chunks per row
+  for (int i = tid; i < R * cpr; i += kBwdRowsThreads) {
+    const int r = i / cpr, c = (i - r * cpr) * NVO;
+    float f[NVO];
+    if (r < r_cap) {
+      const float n = (float)max(counts[(int64_t)b * r_cap + r], 1);
+      const TIn* src = dout + ((int64_t)b * R + r) * D + c;
+      if constexpr (NVO == 8) {
+        load8(src, f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < NVO; ++e) f[e] = Elem<TIn>::ld(src + e);
+      }
+#pragma unroll
+      for (int e = 0; e < NVO; ++e) f[e] = f[e] / n;
+    } else {
+#pragma unroll
+      for (int e = 0; e < NVO; ++e) f[e] = 0.f;
+    }
+    if constexpr (NVO == 8) store8(s_g + (size_t)r * D + c, f);
+    else *reinterpret_cast<float4*>(s_g + (size_t)r * D + c) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  __syncthreads();
+  uint4* o = reinterpret_cast<uint4*>(dx + ((int64_t)b * P + p0) * D);
+  const int total = (p1 - p0) * cpr;
+  int row = tid / cpr, cc = tid - row * cpr;            // kBwdRowsThreads / cpr and % cpr advance (row, cc) per step
+  const int drow = kBwdRowsThreads / cpr, dcc = kBwdRowsThreads - drow * cpr;
+#pragma unroll 4
+  for (int i = tid; i < total; i += kBwdRowsThreads) {
+    const int r = s_slot[row];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r >= 0) v = *reinterpret_cast<const uint4*>(s_g + (size_t)r * D + cc * NVO);
+    o[i] = v;
+    row += drow;
+    cc += dcc;
+    if (cc >= cpr) { cc -= cpr; ++row; }
+  }
+}
+
 // =====================================================================================================
 // 'max' and 'attention' pooling (models/sppp.py:178-184 / 211-216): the non-default SuperpixelPooling variants.
 // One 128-thread CTA per (image, slot) walks the slot's CSR list in ascending patch order; threads own columns.
@@ -1273,6 +1336,33 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
 template <typename TIn, typename TOut>
 int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts, void* dx, int B, int P, int R,
                     int D, int r_cap, cudaStream_t st) {
+  // (a) whole rows per CTA when the image's R gradient rows fit in shared memory (every model configuration)
+  {
+    constexpr int NVO = 16 / (int)sizeof(TOut);
+    const size_t gbytes = (size_t)R * D * sizeof(TOut);
+    const bool in_vec = sizeof(TIn) == 4 || (((uintptr_t)dout % 16 == 0) && (D % 8 == 0));
+    if (((uintptr_t)dx % 16 == 0) && (D % NVO == 0) && in_vec && gbytes <= 96 * 1024 && D / NVO <= kBwdRowsThreads) {
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (gbytes + 2048)));
+      int nchunks = ceil_div(per_sm * num_sms(), B);                 // enough CTAs to fill the machine once ...
+      nchunks = std::max(1, std::min(nchunks, ceil_div(P, 16)));     // ... with at least 16 rows each
+      const int rows = ceil_div(P, nchunks);
+      nchunks = ceil_div(P, rows);
+      const size_t smem_r = gbytes + (size_t)rows * 4;
+      if ((int64_t)B * nchunks < INT_MAX) {
+        static bool configured_r = false;  // per instantiation
+        if (!configured_r) {
+          FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_bwd_rows_kernel<TIn, TOut>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+          configured_r = true;
+        }
+        note_kernel("sppp_pool_bwd_rows_kernel grid=%d rows=%d", B * nchunks, rows);
+        sppp_pool_bwd_rows_kernel<TIn, TOut><<<(unsigned)(B * nchunks), kBwdRowsThreads, smem_r, st>>>(
+            (const TIn*)dout, slot, counts, (TOut*)dx, P, R, D, r_cap, nchunks, rows);
+        FAVIT_CHECK_LAUNCH();
+        return FAVIT_OK;
+      }
+    }
+  }
   const size_t smem = (size_t)R * kBwdCols * sizeof(float) + (size_t)P * 4;
   const int nslices = ceil_div(D, kBwdCols);
   if (((uintptr_t)dx % 16 == 0) && (((size_t)D * sizeof(TOut)) % 16 == 0) && smem <= 160 * 1024 &&

@@ -40,20 +40,43 @@ __global__ void __launch_bounds__(256) sppp_pool_pixels_kernel(const float* __re
   __syncthreads();
   const float inv = 1.f / (float)max(n, 1);
   const int pp = ps * ps;
-  for (int e = threadIdx.x; e < F; e += blockDim.x) {
-    const int c = e / pp, rem = e - c * pp;
-    const int p1 = rem / ps, p2 = rem - p1 * ps;
-    const float* base = img + ((int64_t)(b * C + c) * img_h + p1) * img_w + p2;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains: loads in flight, fixed summation order
+  // EU features per thread side by side, four patches each per round: up to 12 independent 4-byte loads in flight per
+  // thread (the kernel is a latency-bound gather of 64-byte segments; bytes in flight are what buys bandwidth).  The
+  // summation order per feature is fixed: (t mod 4) partial sums, combined pairwise.
+  constexpr int EU = 3;
+  for (int e0 = threadIdx.x; e0 < F; e0 += EU * (int)blockDim.x) {
+    const float* base[EU];
+    int dst[EU];
+    float a[EU][4];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      const int e = min(e0 + u * (int)blockDim.x, F - 1);   // clamped duplicates are computed and discarded
+      const int c = e / pp, rem = e - c * pp;
+      const int p1 = rem / ps, p2 = rem - p1 * ps;
+      base[u] = img + ((int64_t)(b * C + c) * img_h + p1) * img_w + p2;
+      dst[u] = e0 + u * (int)blockDim.x < F ? (p1 * ps + p2) * C + c : -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[u][k] = 0.f;
+    }
     int t = 0;
     for (; t + 4 <= n; t += 4) {
-      a0 += __ldg(base + s_off[t]);
-      a1 += __ldg(base + s_off[t + 1]);
-      a2 += __ldg(base + s_off[t + 2]);
-      a3 += __ldg(base + s_off[t + 3]);
+      const int o0 = s_off[t], o1 = s_off[t + 1], o2 = s_off[t + 2], o3 = s_off[t + 3];
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        a[u][0] += __ldg(base[u] + o0);
+        a[u][1] += __ldg(base[u] + o1);
+        a[u][2] += __ldg(base[u] + o2);
+        a[u][3] += __ldg(base[u] + o3);
+      }
     }
-    for (; t < n; ++t) a0 += __ldg(base + s_off[t]);
-    s_out[(p1 * ps + p2) * C + c] = ((a0 + a1) + (a2 + a3)) * inv;
+    for (; t < n; ++t) {
+      const int o0 = s_off[t];
+#pragma unroll
+      for (int u = 0; u < EU; ++u) a[u][0] += __ldg(base[u] + o0);
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u)
+      if (dst[u] >= 0) s_out[dst[u]] = ((a[u][0] + a[u][1]) + (a[u][2] + a[u][3])) * inv;
   }
   __syncthreads();
   TOut* o = out + (int64_t)blockIdx.x * F;
@@ -90,12 +113,15 @@ extern "C" int favit_sppp_pool_pixels(const float* image, int B, int C, int img_
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  note_kernel("sppp_pool_pixels_kernel grid=%d", B * R);
+  // three features per thread (EU in the kernel): narrow pixel patches get narrower CTAs instead of idle or duplicate lanes
+  int threads = ((patch * patch * C + 2) / 3 + 31) / 32 * 32;
+  threads = threads < 32 ? 32 : (threads > 256 ? 256 : threads);
+  note_kernel("sppp_pool_pixels_kernel grid=%d threads=%d", B * R, threads);
   if (out_dtype == FAVIT_BF16)
-    sppp_pool_pixels_kernel<__nv_bfloat16><<<(unsigned)(B * R), 256, smem, st>>>(
+    sppp_pool_pixels_kernel<__nv_bfloat16><<<(unsigned)(B * R), threads, smem, st>>>(
         image, order, offsets, num_slots, (__nv_bfloat16*)out, C, img_h, img_w, patch, grid, P, R, r_cap);
   else if (out_dtype == FAVIT_F32)
-    sppp_pool_pixels_kernel<float><<<(unsigned)(B * R), 256, smem, st>>>(image, order, offsets, num_slots, (float*)out, C,
+    sppp_pool_pixels_kernel<float><<<(unsigned)(B * R), threads, smem, st>>>(image, order, offsets, num_slots, (float*)out, C,
                                                                         img_h, img_w, patch, grid, P, R, r_cap);
   else { set_error("sppp_pool_pixels: bad dtype"); return FAVIT_ERR_ARG; }
   FAVIT_CHECK_LAUNCH();

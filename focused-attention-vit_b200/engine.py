@@ -28,12 +28,15 @@ class TrainStep:
         backward hooks and running beside the rest of backward (also inside the captured graph); "deferred" = one
         coalesced all-reduce of every gradient after backward (inside the graph when cuda_graph); "split" = deferred, with
         the collective issued eagerly between two graphs (backward | AdamW), for NCCL builds that cannot be captured."""
-        if dp_mode not in ("overlap", "deferred", "split"):
+        if dp_mode not in ("overlap", "deferred", "split", "none"):
             raise ValueError(f"unknown dp_mode {dp_mode!r}")
         self.dp_mode = dp_mode
         self.model = model
         self.autocast_dtype = autocast_dtype
-        self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group)
+        # "none": DIAGNOSTIC ONLY (bench.py --dp-mode none): ranks train independently, no gradient exchange — what N ranks
+        # cost without any collective (clock / power skew between the GPUs of a box)
+        self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group,
+                                      enabled=False if dp_mode == "none" else None)
         self.reducer.overlap = dp_mode == "overlap"
         # lr / weight decay: the reference's defaults (main.py:129-132).  optimizer: True / "favit" = the multi-tensor
         # AdamW kernel of this library (optim.FusedAdamW; `param_groups` = e.g. optim.reference_param_groups for the three
