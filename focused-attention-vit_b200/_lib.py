@@ -26,6 +26,7 @@ _SIGS = {
     "favit_launch_count": ([], _u64),
     "favit_mhla_attn_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i64, _i64, _i64, _i, _f, _u64, _vp], _i),
     "favit_cast_bf16_batched": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp], _i),
+    "favit_copy_batched": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _vp], _i),
     "favit_colsum": ([_vp, _i, _vp, _i, _i, _i64, _vp], _i),
     "favit_mhla_attn_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f,
                              _i64, _i64, _i64, _i, _f, _u64, _vp], _i),

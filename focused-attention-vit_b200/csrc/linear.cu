@@ -270,18 +270,19 @@ extern "C" int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const v
   return tc::gemm_bf16(a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, M, N, K, e, bn, splits, (cudaStream_t)stream);
 }
 
-// ---- fp32 master weights -> bf16 GEMM operands, many tensors per launch ---------------------------------------
+// ---- many tensors per launch: fp32 master weights -> bf16 GEMM operands, small gradients <-> a flat all-reduce buffer ----
 namespace favit {
 namespace {
 constexpr int kCastMax = 32;
 struct CastTable {
-  const float* src[kCastMax];
-  __nv_bfloat16* dst[kCastMax];
+  const void* src[kCastMax];
+  void* dst[kCastMax];
   int64_t n[kCastMax];
 };
-__global__ void __launch_bounds__(256) cast_bf16_batched_kernel(const __grid_constant__ CastTable t) {
-  const float* s = t.src[blockIdx.y];
-  __nv_bfloat16* d = t.dst[blockIdx.y];
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) copy_batched_kernel(const __grid_constant__ CastTable t) {
+  const TS* s = (const TS*)t.src[blockIdx.y];
+  TD* d = (TD*)t.dst[blockIdx.y];
   const int64_t n = t.n[blockIdx.y];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
   const bool vec = ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0);
@@ -291,37 +292,55 @@ __global__ void __launch_bounds__(256) cast_bf16_batched_kernel(const __grid_con
       load8(s + i, f);
       store8(d + i, f);
     } else {
-      for (int64_t k = i; k < n && k < i + 8; ++k) d[k] = __float2bfloat16_rn(s[k]);
+      for (int64_t k = i; k < n && k < i + 8; ++k) Elem<TD>::st(d + k, Elem<TS>::ld(s + k));
     }
   }
 }
-}  // namespace
-}  // namespace favit
 
-// dst[t][0..n[t]) = bf16(src[t][0..n[t])) for `count` tensors (host arrays): the per-step cast of the fp32 master
-// weights (models/vit.py:107-139 fc1 / fc2 of every block) as one launch per 32 tensors instead of one per tensor.
-extern "C" int favit_cast_bf16_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
-                                       favit_stream stream) {
-  FAVIT_CHECK_ARG(count > 0 && src && dst && numel, "cast_bf16_batched: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
+template <typename TS, typename TD>
+int launch_copy_batched(int count, const void* const* src, void* const* dst, const int64_t* numel, cudaStream_t st) {
   for (int t0 = 0; t0 < count; t0 += kCastMax) {
     const int n = count - t0 < kCastMax ? count - t0 : kCastMax;
     CastTable t;
     int64_t big = 0;
     for (int i = 0; i < kCastMax; ++i) {
       const int k = i < n ? t0 + i : t0;  // unused rows repeat the first tensor with length 0
-      FAVIT_CHECK_ARG(src[k] && dst[k] && numel[k] >= 0, "cast_bf16_batched: null tensor %d", k);
-      t.src[i] = (const float*)src[k];
-      t.dst[i] = (__nv_bfloat16*)dst[k];
+      FAVIT_CHECK_ARG(src[k] && dst[k] && numel[k] >= 0, "copy_batched: null tensor %d", k);
+      t.src[i] = src[k];
+      t.dst[i] = dst[k];
       t.n[i] = i < n ? numel[k] : 0;
       big = t.n[i] > big ? t.n[i] : big;
     }
     int bx = (int)((big + 2047) / 2048);
     bx = bx < 1 ? 1 : (bx > 4 * num_sms() ? 4 * num_sms() : bx);
-    cast_bf16_batched_kernel<<<dim3(bx, n), 256, 0, st>>>(t);
+    copy_batched_kernel<TS, TD><<<dim3(bx, n), 256, 0, st>>>(t);
     FAVIT_CHECK_LAUNCH();
   }
   return FAVIT_OK;
+}
+}  // namespace
+}  // namespace favit
+
+// dst[t][0..n[t]) = convert(src[t][0..n[t])) for `count` tensors (host arrays of device pointers / sizes), one launch per
+// 32 tensors.  Uses: the per-step cast of the fp32 master weights of the MLP (models/vit.py:107-139 fc1 / fc2 of every
+// block) into bf16 GEMM operands, and packing the ~100 small gradients of a model (biases, LayerNorm parameters) into one
+// flat buffer — and back — so that the data-parallel all-reduce handles one tensor instead of a hundred.
+extern "C" int favit_copy_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
+                                  favit_dtype src_dtype, favit_dtype dst_dtype, favit_stream stream) {
+  FAVIT_CHECK_ARG(count > 0 && src && dst && numel, "copy_batched: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == FAVIT_F32 && dst_dtype == FAVIT_BF16) return launch_copy_batched<float, __nv_bfloat16>(count, src, dst, numel, st);
+  if (src_dtype == FAVIT_BF16 && dst_dtype == FAVIT_F32) return launch_copy_batched<__nv_bfloat16, float>(count, src, dst, numel, st);
+  if (src_dtype == FAVIT_F32 && dst_dtype == FAVIT_F32) return launch_copy_batched<float, float>(count, src, dst, numel, st);
+  if (src_dtype == FAVIT_BF16 && dst_dtype == FAVIT_BF16)
+    return launch_copy_batched<__nv_bfloat16, __nv_bfloat16>(count, src, dst, numel, st);
+  set_error("copy_batched: bad dtype");
+  return FAVIT_ERR_ARG;
+}
+
+extern "C" int favit_cast_bf16_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
+                                       favit_stream stream) {
+  return favit_copy_batched(count, src, dst, numel, FAVIT_F32, FAVIT_BF16, stream);
 }
 
 // out[n] += sum_m x[m,n]   (accumulates: zero `out` first for a plain column sum)

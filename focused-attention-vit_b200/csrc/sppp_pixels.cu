@@ -16,7 +16,9 @@
 namespace favit {
 namespace {
 
-template <typename TOut>
+// VEC = 4: a thread owns four consecutive pixels of a patch row (one 16-byte load per patch; needs patch % 4 == 0,
+// img_w % 4 == 0 and a 16-byte aligned image), VEC = 1: one pixel (any geometry).
+template <typename TOut, int VEC>
 __global__ void __launch_bounds__(256) sppp_pool_pixels_kernel(const float* __restrict__ img,
                                                                const int32_t* __restrict__ order,
                                                                const int32_t* __restrict__ offsets,
@@ -40,43 +42,46 @@ __global__ void __launch_bounds__(256) sppp_pool_pixels_kernel(const float* __re
   __syncthreads();
   const float inv = 1.f / (float)max(n, 1);
   const int pp = ps * ps;
-  // EU features per thread side by side, four patches each per round: up to 12 independent 4-byte loads in flight per
-  // thread (the kernel is a latency-bound gather of 64-byte segments; bytes in flight are what buys bandwidth).  The
-  // summation order per feature is fixed: (t mod 4) partial sums, combined pairwise.
-  constexpr int EU = 3;
-  for (int e0 = threadIdx.x; e0 < F; e0 += EU * (int)blockDim.x) {
-    const float* base[EU];
-    int dst[EU];
-    float a[EU][4];
+  // The kernel is a latency-bound gather of short segments (ps consecutive floats per patch row): bytes in flight are
+  // what buys bandwidth, so every thread keeps UN independent loads going (UN patches of its own pixel group).  The
+  // summation order per feature is fixed: (t mod UN) partial sums, combined in a fixed tree.
+  constexpr int UN = 8;
+  const int groups = F / VEC;   // pixel groups in memory order (c, p1, p2 / VEC)
+  for (int e = threadIdx.x; e < groups; e += blockDim.x) {
+    const int q = e * VEC;
+    const int c = q / pp, rem = q - c * pp;
+    const int p1 = rem / ps, p2 = rem - p1 * ps;
+    const float* base = img + ((int64_t)(b * C + c) * img_h + p1) * img_w + p2;
+    float a[UN][VEC];
 #pragma unroll
-    for (int u = 0; u < EU; ++u) {
-      const int e = min(e0 + u * (int)blockDim.x, F - 1);   // clamped duplicates are computed and discarded
-      const int c = e / pp, rem = e - c * pp;
-      const int p1 = rem / ps, p2 = rem - p1 * ps;
-      base[u] = img + ((int64_t)(b * C + c) * img_h + p1) * img_w + p2;
-      dst[u] = e0 + u * (int)blockDim.x < F ? (p1 * ps + p2) * C + c : -1;
+    for (int k = 0; k < UN; ++k)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a[u][k] = 0.f;
-    }
+      for (int v = 0; v < VEC; ++v) a[k][v] = 0.f;
     int t = 0;
-    for (; t + 4 <= n; t += 4) {
-      const int o0 = s_off[t], o1 = s_off[t + 1], o2 = s_off[t + 2], o3 = s_off[t + 3];
+    for (; t + UN <= n; t += UN) {
 #pragma unroll
-      for (int u = 0; u < EU; ++u) {
-        a[u][0] += __ldg(base[u] + o0);
-        a[u][1] += __ldg(base[u] + o1);
-        a[u][2] += __ldg(base[u] + o2);
-        a[u][3] += __ldg(base[u] + o3);
+      for (int k = 0; k < UN; ++k) {
+        if constexpr (VEC == 4) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(base + s_off[t + k]));
+          a[k][0] += x.x; a[k][1] += x.y; a[k][2] += x.z; a[k][3] += x.w;
+        } else {
+          a[k][0] += __ldg(base + s_off[t + k]);
+        }
       }
     }
     for (; t < n; ++t) {
-      const int o0 = s_off[t];
-#pragma unroll
-      for (int u = 0; u < EU; ++u) a[u][0] += __ldg(base[u] + o0);
+      if constexpr (VEC == 4) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(base + s_off[t]));
+        a[0][0] += x.x; a[0][1] += x.y; a[0][2] += x.z; a[0][3] += x.w;
+      } else {
+        a[0][0] += __ldg(base + s_off[t]);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < EU; ++u)
-      if (dst[u] >= 0) s_out[dst[u]] = ((a[u][0] + a[u][1]) + (a[u][2] + a[u][3])) * inv;
+    for (int v = 0; v < VEC; ++v) {
+      const float sum = ((a[0][v] + a[1][v]) + (a[2][v] + a[3][v])) + ((a[4][v] + a[5][v]) + (a[6][v] + a[7][v]));
+      s_out[(p1 * ps + p2 + v) * C + c] = sum * inv;
+    }
   }
   __syncthreads();
   TOut* o = out + (int64_t)blockIdx.x * F;
@@ -105,25 +110,28 @@ extern "C" int favit_sppp_pool_pixels(const float* image, int B, int C, int img_
     return FAVIT_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (patch % 4 == 0) && (img_w % 4 == 0) && ((uintptr_t)image % 16 == 0);
   static bool configured = false;
   if (!configured) {
-    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
-    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<__nv_bfloat16>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(sppp_pool_pixels_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  // three features per thread (EU in the kernel): narrow pixel patches get narrower CTAs instead of idle or duplicate lanes
-  int threads = ((patch * patch * C + 2) / 3 + 31) / 32 * 32;
+  // one pixel group per thread: narrow pixel patches get narrower CTAs instead of idle lanes
+  int threads = (patch * patch * C / (vec ? 4 : 1) + 31) / 32 * 32;
   threads = threads < 32 ? 32 : (threads > 256 ? 256 : threads);
-  note_kernel("sppp_pool_pixels_kernel grid=%d threads=%d", B * R, threads);
-  if (out_dtype == FAVIT_BF16)
-    sppp_pool_pixels_kernel<__nv_bfloat16><<<(unsigned)(B * R), threads, smem, st>>>(
-        image, order, offsets, num_slots, (__nv_bfloat16*)out, C, img_h, img_w, patch, grid, P, R, r_cap);
-  else if (out_dtype == FAVIT_F32)
-    sppp_pool_pixels_kernel<float><<<(unsigned)(B * R), threads, smem, st>>>(image, order, offsets, num_slots, (float*)out, C,
-                                                                        img_h, img_w, patch, grid, P, R, r_cap);
-  else { set_error("sppp_pool_pixels: bad dtype"); return FAVIT_ERR_ARG; }
+  note_kernel("sppp_pool_pixels_kernel<VEC=%d> grid=%d threads=%d", vec ? 4 : 1, B * R, threads);
+#define FAVIT_PIX(T, V)                                                                                              \
+  sppp_pool_pixels_kernel<T, V><<<(unsigned)(B * R), threads, smem, st>>>(image, order, offsets, num_slots, (T*)out, C, \
+                                                                         img_h, img_w, patch, grid, P, R, r_cap)
+  if (out_dtype == FAVIT_BF16) {
+    if (vec) FAVIT_PIX(__nv_bfloat16, 4); else FAVIT_PIX(__nv_bfloat16, 1);
+  } else if (out_dtype == FAVIT_F32) {
+    if (vec) FAVIT_PIX(float, 4); else FAVIT_PIX(float, 1);
+  } else { set_error("sppp_pool_pixels: bad dtype"); return FAVIT_ERR_ARG; }
+#undef FAVIT_PIX
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }

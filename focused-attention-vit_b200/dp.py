@@ -86,6 +86,8 @@ class NcclComm:
 
 
 class GradAllReducer:
+    SMALL = 65536      # gradients below this many elements are packed into one flat buffer per all-reduce
+
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 32.0, process_group=None,
                  enabled: Optional[bool] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -102,6 +104,7 @@ class GradAllReducer:
         self.overlap = True          # False: hooks are silent and finish() reduces everything in one grouped call
         self.collectives = 0         # all-reduce launches issued since construction
         self.nccl: Optional[NcclComm] = None
+        self._flat = {}
         if not self.enabled:
             return
         for p in self.params:
@@ -139,13 +142,32 @@ class GradAllReducer:
             self._pending = [len(b) for b in self.buckets]
             self._works = []
 
-    def _reduce(self, tensors: List[torch.Tensor]):
+    def _reduce(self, tensors: List[torch.Tensor], key=None):
+        """One grouped all-reduce.  On NCCL the SMALL tensors of the set (biases, LayerNorm parameters: ~100 of a ViT's
+        ~150 gradients, a few KB each) travel as ONE flat buffer — packed and unpacked by a multi-tensor copy kernel —
+        because every member of a NCCL group is a collective of its own with its own latency; the large weight
+        gradients are reduced in place.  Returns (completion handle, tensors, unpack job or None)."""
         self.collectives += 1
         if self.nccl is not None:
-            return self.nccl.all_reduce_avg(tensors), tensors
+            small = [t for t in tensors if t.numel() < self.SMALL]
+            if len(small) < 2:
+                return self.nccl.all_reduce_avg(tensors), tensors, None
+            from . import raw
+            flat = self._flat.get(key)
+            total = sum((t.numel() + 3) // 4 * 4 for t in small)
+            if flat is None or flat.numel() != total:
+                flat = torch.empty(total, dtype=torch.float32, device=small[0].device)
+                self._flat[key] = flat
+            views, off = [], 0
+            for t in small:
+                views.append(flat[off:off + t.numel()])
+                off += (t.numel() + 3) // 4 * 4
+            raw.copy_batched(small, views)
+            big = [t for t in tensors if t.numel() >= self.SMALL]
+            return self.nccl.all_reduce_avg(big + [flat]), tensors, (views, small)
         opts = dist.AllreduceCoalescedOptions()
         opts.reduceOp = dist.ReduceOp.SUM          # gloo has no AVG: sum and scale afterwards
-        return self._pg.allreduce_coalesced(tensors, opts), tensors
+        return self._pg.allreduce_coalesced(tensors, opts), tensors, None
 
     def _hook(self, p: torch.nn.Parameter) -> None:
         if not self.overlap:
@@ -153,7 +175,7 @@ class GradAllReducer:
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
-            self._works.append(self._reduce([q.grad for q in self.buckets[bi]]))
+            self._works.append(self._reduce([q.grad for q in self.buckets[bi]], key=bi))
 
     def finish(self) -> None:
         """Reduce what the hooks have not (deferred mode: everything, in one grouped call; overlapped mode: buckets
@@ -164,17 +186,20 @@ class GradAllReducer:
         if not self.overlap:
             left = [p.grad for p in self.params if p.grad is not None]
             if left:
-                self._works.append(self._reduce(left))
+                self._works.append(self._reduce(left, key="all"))
         else:
             for bi, n in enumerate(self._pending):
                 if n != 0:
                     left = [p.grad for p in self.buckets[bi] if p.grad is not None]
                     if left:
-                        self._works.append(self._reduce(left))
+                        self._works.append(self._reduce(left, key=("rest", bi)))
         self._pending = [0] * len(self._pending)
-        for w, tensors in self._works:
+        for w, tensors, unpack in self._works:
             if self.nccl is not None:
                 torch.cuda.current_stream().wait_event(w)
+                if unpack is not None:
+                    from . import raw
+                    raw.copy_batched(*unpack)           # flat buffer -> the small gradients, on the compute stream
             else:
                 w.wait()
                 torch._foreach_div_(tensors, float(self.world))

@@ -184,6 +184,19 @@ def cast_bf16_batched(tensors):
     return outs
 
 
+def copy_batched(srcs, dsts) -> None:
+    """dsts[i][...] = srcs[i] (fp32 / bf16, converted if the dtypes differ; all srcs one dtype, all dsts one dtype),
+    one launch per 32 tensors.  Tensors must be contiguous."""
+    import ctypes as C
+    n = len(srcs)
+    if n == 0:
+        return
+    rc = L.call("copy", 0.0, L.lib().favit_copy_batched, n, (C.c_void_p * n)(*[t.data_ptr() for t in srcs]),
+                (C.c_void_p * n)(*[t.data_ptr() for t in dsts]), (C.c_int64 * n)(*[t.numel() for t in srcs]),
+                _DT[srcs[0].dtype], _DT[dsts[0].dtype], _s())
+    L.check(rc, "favit_copy_batched")
+
+
 def fold_fwd_batched(layers, H: int, cd: torch.dtype):
     """layers: list of (qkv_w, qkv_b, proj_w, proj_b, lat_w, lat_b) fp32 tensors of the L blocks of one model.
     One call for the whole model; returns L tuples (wqkv' cd, bqkv' fp32, wproj' cd, bproj' fp32), views of four

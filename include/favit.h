@@ -152,6 +152,10 @@ int favit_colsum(const void* x, favit_dtype dtype, float* out, int M, int N, int
  * arrays of device pointers / element counts. */
 int favit_cast_bf16_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
                             favit_stream stream);
+/* The same with any of the four fp32 / bf16 conversions (fp32 -> fp32 is a plain multi-tensor copy): also packs the small
+ * gradients of a model into one flat buffer, and unpacks them, around the data-parallel all-reduce. */
+int favit_copy_batched(int count, const void* const* src, void* const* dst, const int64_t* numel,
+                       favit_dtype src_dtype, favit_dtype dst_dtype, favit_stream stream);
 
 /* Test / tuning hook: C[M,N] = A.B^T through the tcgen05 kernel with explicit operand storage
  * (a_mn / b_mn: 0 = reduction dimension contiguous, 1 = M/N dimension contiguous), tile width
