@@ -435,7 +435,8 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     model = build_model(wl, device)
     if wl["kind"] == "sppp":
         model.validate_slots = False          # synthetic maps are validated once, below, not once per step
-    step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph, dp_mode=args.dp_mode)
+    step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph, dp_mode=args.dp_mode,
+                     dp_grad_dtype=torch.bfloat16 if args.dp_grad_dtype == "bf16" else torch.float32)
     # distinct batches so that no step can reuse a cached input; seed differs per rank
     nb = 2
     batches = [make_batch(wl, B, seed=1234 + rank * 100 + i, device=device) for i in range(nb)]
@@ -596,6 +597,7 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
                    "superpixels": wl.get("K"), "parallelism": f"dp{world}", "optimizer": "favit multi-tensor AdamW kernel, in step", "cuda_graph": bool(args.cuda_graph),
                    "dp_mode": (args.dp_mode + (" (NCCL all-reduce nodes inside the step graph)" if args.cuda_graph and
                                                args.dp_mode != "split" else "")) if dist_on else None,
+                   "dp_grad_dtype": args.dp_grad_dtype if dist_on else None,
                    "grad_allreduce_calls_per_step": (len(step.reducer.buckets) if args.dp_mode == "overlap" else 1)
                    if dist_on else 0,
                    "l2": "working set >> L2 every step (inputs %.0f MB, activations several GB); no flush needed"
@@ -635,6 +637,8 @@ def main():
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true",
                     help="capture the training step in a CUDA graph (default)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    ap.add_argument("--dp-grad-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="dtype of the gradients on the wire (bf16 = one flat bf16 buffer, half the NVLink bytes)")
     ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
                     help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
                          "(default), one collective after backward, or one collective outside the step graph")

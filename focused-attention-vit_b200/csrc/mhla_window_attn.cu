@@ -28,6 +28,11 @@ int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, con
                  int64_t shh, cudaStream_t st);
 // tensor-core tile path (mhla_window_attn_mma.cu)
 bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* mask);
+// mhla_window_attn_tc.cu: tcgen05 / TMEM forward for wide windows (17 <= W <= 65, head_dim 64, bf16, N >= W)
+bool attn_tc_applicable(int hd, int window, int N, favit_dtype dtype, const uint8_t* mask, const void* q, const void* k,
+                        const void* v, int64_t sb, int64_t sn, int64_t shh);
+int attn_tc_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
+                float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
 int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
                  int window, float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
 int attn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
@@ -419,6 +424,11 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
       ((uintptr_t)out % 16) == 0) {
     note_kernel("attn_seq_fwd (TMA whole-sequence, mma.sync)");
     return attn_seq_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
+  }
+  if (!drop && attn_tc_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
+      ((uintptr_t)out % 16) == 0) {
+    note_kernel("attn_tc_fwd (tcgen05 / TMEM, 128-query tiles)");
+    return attn_tc_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
   }
   if (!drop && attn_mma_applicable(hd, window, dtype, mask)) {
     note_kernel("attn_mma_fwd (per-warp staging, mma.sync)");

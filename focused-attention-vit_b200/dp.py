@@ -28,7 +28,7 @@ from typing import Iterable, List, Optional
 import torch
 import torch.distributed as dist
 
-_NCCL_FLOAT32, _NCCL_AVG, _NCCL_SUM = 7, 4, 0
+_NCCL_FLOAT32, _NCCL_BFLOAT16, _NCCL_AVG, _NCCL_SUM = 7, 9, 4, 0
 
 
 class _UniqueId(C.Structure):
@@ -70,10 +70,11 @@ class NcclComm:
         st = C.c_void_p(self.stream.cuda_stream)
         self._check(self.lib.ncclGroupStart(), "ncclGroupStart")
         for t in tensors:
-            if not t.is_contiguous() or t.dtype != torch.float32:
-                raise TypeError("NcclComm.all_reduce_avg takes contiguous fp32 tensors")
+            if not t.is_contiguous() or t.dtype not in (torch.float32, torch.bfloat16):
+                raise TypeError("NcclComm.all_reduce_avg takes contiguous fp32 / bf16 tensors")
             p = C.c_void_p(t.data_ptr())
-            self._check(self.lib.ncclAllReduce(p, p, t.numel(), _NCCL_FLOAT32, _NCCL_AVG, self.comm, st), "ncclAllReduce")
+            dt = _NCCL_FLOAT32 if t.dtype == torch.float32 else _NCCL_BFLOAT16
+            self._check(self.lib.ncclAllReduce(p, p, t.numel(), dt, _NCCL_AVG, self.comm, st), "ncclAllReduce")
         self._check(self.lib.ncclGroupEnd(), "ncclGroupEnd")
         ev = torch.cuda.Event()
         ev.record(self.stream)
@@ -89,7 +90,14 @@ class GradAllReducer:
     SMALL = 65536      # gradients below this many elements are packed into one flat buffer per all-reduce
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 32.0, process_group=None,
-                 enabled: Optional[bool] = None):
+                 enabled: Optional[bool] = None, grad_dtype: torch.dtype = torch.float32):
+        """grad_dtype=torch.bfloat16 (NCCL only): the gradients cross NVLink as ONE flat bf16 buffer per all-reduce (half
+        the bytes; packed from / unpacked into the fp32 .grad tensors by the multi-tensor copy kernel, the reduction
+        itself accumulates in fp32 inside NCCL).  The averaged gradient is then rounded to bf16 — a data-parallel design
+        choice like DDP's bf16 compression hook, off by default: fp32 keeps the 1e-5 equality with the large batch."""
+        if grad_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("grad_dtype must be torch.float32 or torch.bfloat16")
+        self.grad_dtype = grad_dtype
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = process_group
         if enabled is None:
@@ -149,21 +157,21 @@ class GradAllReducer:
         gradients are reduced in place.  Returns (completion handle, tensors, unpack job or None)."""
         self.collectives += 1
         if self.nccl is not None:
-            small = [t for t in tensors if t.numel() < self.SMALL]
-            if len(small) < 2:
+            small = tensors if self.grad_dtype == torch.bfloat16 else [t for t in tensors if t.numel() < self.SMALL]
+            if len(small) < 2 and self.grad_dtype == torch.float32:
                 return self.nccl.all_reduce_avg(tensors), tensors, None
             from . import raw
             flat = self._flat.get(key)
-            total = sum((t.numel() + 3) // 4 * 4 for t in small)
-            if flat is None or flat.numel() != total:
-                flat = torch.empty(total, dtype=torch.float32, device=small[0].device)
+            total = sum((t.numel() + 7) // 8 * 8 for t in small)          # 16-byte aligned views
+            if flat is None or flat.numel() != total or flat.dtype != self.grad_dtype:
+                flat = torch.empty(total, dtype=self.grad_dtype, device=small[0].device)
                 self._flat[key] = flat
             views, off = [], 0
             for t in small:
                 views.append(flat[off:off + t.numel()])
-                off += (t.numel() + 3) // 4 * 4
+                off += (t.numel() + 7) // 8 * 8
             raw.copy_batched(small, views)
-            big = [t for t in tensors if t.numel() >= self.SMALL]
+            big = [] if self.grad_dtype == torch.bfloat16 else [t for t in tensors if t.numel() >= self.SMALL]
             return self.nccl.all_reduce_avg(big + [flat]), tensors, (views, small)
         opts = dist.AllreduceCoalescedOptions()
         opts.reduceOp = dist.ReduceOp.SUM          # gloo has no AVG: sum and scale afterwards

@@ -23,7 +23,8 @@ class TrainStep:
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.05,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 32.0,
-                 optimizer=True, cuda_graph: bool = False, dp_mode: str = "overlap", param_groups=None):
+                 optimizer=True, cuda_graph: bool = False, dp_mode: str = "overlap", param_groups=None,
+                 dp_grad_dtype: torch.dtype = torch.float32):
         """dp_mode (data parallel only): "overlap" = one coalesced all-reduce per gradient bucket, launched from the
         backward hooks and running beside the rest of backward (also inside the captured graph); "deferred" = one
         coalesced all-reduce of every gradient after backward (inside the graph when cuda_graph); "split" = deferred, with
@@ -36,7 +37,7 @@ class TrainStep:
         # "none": DIAGNOSTIC ONLY (bench.py --dp-mode none): ranks train independently, no gradient exchange — what N ranks
         # cost without any collective (clock / power skew between the GPUs of a box)
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group,
-                                      enabled=False if dp_mode == "none" else None)
+                                      enabled=False if dp_mode == "none" else None, grad_dtype=dp_grad_dtype)
         self.reducer.overlap = dp_mode == "overlap"
         # lr / weight decay: the reference's defaults (main.py:129-132).  optimizer: True / "favit" = the multi-tensor
         # AdamW kernel of this library (optim.FusedAdamW; `param_groups` = e.g. optim.reference_param_groups for the three

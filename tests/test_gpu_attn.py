@@ -160,3 +160,58 @@ def test_module_attention_dropout_statistics():
     xg = x.clone().requires_grad_(True)
     m(xg).sum().backward()
     assert torch.isfinite(xg.grad).all() and m.latent_proj.weight.grad is not None
+
+
+# wide windows: forward on the tcgen05 / TMEM kernel (mhla_window_attn_tc.cu), backward on the general kernel fed by its LSE
+TC_CASES = [
+    # B, H, N, W
+    (2, 3, 197, 63),      # C4 tokens, two query tiles, the second one ragged
+    (1, 2, 128, 63),      # exactly one tile
+    (1, 2, 129, 31),      # one-row second tile
+    (2, 2, 63, 63),       # N == W: every row but the middle one has duplicated-edge slots
+    (1, 3, 64, 63),
+    (3, 2, 65, 17),       # the narrowest window of this path
+    (1, 2, 300, 33),      # two S chunks per warp at their limit (32 + 2h = 64 columns)
+    (1, 2, 300, 35),      # three chunks
+    (1, 1, 1025, 65),     # the widest window, nine tiles
+    (1, 6, 4097, 63),     # C5-as-ViT tokens
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B{}H{}N{}W{}".format(*c))
+def test_wide_window_tcgen05_forward_matches_oracle(case):
+    from favit_b200 import _lib as L, ops
+    B, H, N, W = case
+    hd = 64
+    torch.manual_seed(N + W)
+    qkv = (torch.randn(B, N, 3, H, hd) * 1.5).to(torch.bfloat16)
+    dout = torch.randn(B, N, H * hd).to(torch.bfloat16)
+    qc = qkv.cuda().requires_grad_(True)
+    out, lse = ops.mhla_attn_fwd(qc.detach(), W, None)
+    assert L.last_kernel().startswith("attn_tc_fwd"), L.last_kernel()
+    q64 = qkv.double().cuda().requires_grad_(True)          # the oracle's closed form, fp64, evaluated on the device
+    q, k, v = [q64[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    o_ref, lse_ref = oracle.mhla_attn_core_closed_form(q, k, v, W, None)
+    o_ref = o_ref.permute(0, 2, 1, 3).reshape(B, N, H * hd)
+    assert_close(out, o_ref, torch.bfloat16, "out")
+    assert_close(lse, lse_ref, torch.bfloat16, "lse")
+    # every output row is a convex combination of V rows
+    vmax = qkv[:, :, 2].float().abs().amax(dim=1).reshape(B, 1, H * hd).cuda()
+    assert bool((out.float().abs() <= vmax * 1.01 + 1e-3).all())
+    # the differentiable op: tcgen05 forward + general backward consuming its LSE
+    out2, _ = ops.mhla_attn(qc, W, None)
+    out2.backward(dout.cuda())
+    (o_ref * dout.double().cuda()).sum().backward()
+    assert torch.equal(out2, out)
+    scale = q64.grad.abs().max().item()
+    for i, nm in enumerate("qkv"):
+        assert_close(qc.grad[:, :, i], q64.grad[:, :, i], torch.bfloat16, "d" + nm, factor=2.0, floor=1e-2 * scale)
+
+
+def test_wide_window_gather_oracle_agrees_on_a_small_case():
+    """The closed form used above against the reference's own gather formulation (mhla.py:109-154) for a wide window."""
+    torch.manual_seed(0)
+    q, k, v = [torch.randn(1, 2, 70, 64, dtype=torch.float64) for _ in range(3)]
+    a = oracle.mhla_attn_core_gather(q, k, v, 63)
+    b, _ = oracle.mhla_attn_core_closed_form(q, k, v, 63)
+    assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)

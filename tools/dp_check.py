@@ -38,10 +38,11 @@ def main():
     ref_g = {k: p.grad.clone() for k, p in ref_m.named_parameters()}
     scale = max(float(v.abs().max()) for v in ref_g.values())
     bad = 0
-    for graph in (False, True):
-        for mode in ("overlap", "deferred", "split"):
+    for graph, mode, gd in [(False, "overlap", torch.float32), (False, "deferred", torch.float32), (True, "overlap", torch.float32),
+                            (True, "deferred", torch.float32), (True, "split", torch.float32), (True, "deferred", torch.bfloat16)]:
+        if True:
             m = model()
-            step = TrainStep(m, lr=0.0, weight_decay=0.0, cuda_graph=graph, dp_mode=mode, bucket_mb=0.5)
+            step = TrainStep(m, lr=0.0, weight_decay=0.0, cuda_graph=graph, dp_mode=mode, bucket_mb=0.5, dp_grad_dtype=gd)
             for _ in range(6 if graph else 2):
                 loss = step(xs, ys)
             torch.cuda.synchronize()
@@ -52,8 +53,10 @@ def main():
             ok = worst < 3e-2          # bf16 compute: shards vs whole batch differ by summation order only
             bad += 0 if ok else 1
             if rank == 0:
-                print(f"graph={graph!s:5} dp_mode={mode:8} buckets={len(step.reducer.buckets):2d} collectives={step.reducer.collectives:3d} "
+                print(f"graph={graph!s:5} dp_mode={mode:8} wire={str(gd)[6:]:8} buckets={len(step.reducer.buckets):2d} collectives={step.reducer.collectives:3d} "
                       f"worst rel grad err vs whole batch {worst:.2e} {'ok' if ok else 'MISMATCH'}", flush=True)
+            step.recapture()             # a captured graph keeps its NCCL kernels alive: drop it before the communicator
+            torch.cuda.synchronize()
             step.reducer.remove()
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
