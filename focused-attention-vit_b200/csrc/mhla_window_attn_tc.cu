@@ -21,6 +21,7 @@
 // core is what keeps the contraction off the critical path that the CUDA-core kernel (4 N W D FMAs) sits on.
 #include <math_constants.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "favit_common.cuh"
@@ -97,34 +98,47 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// The softmax of one warp: WI = warp index (compile time: register arrays must be indexed by constants),
-// NCH = 32-column chunks of S a warp has to read (its rows 32 WI .. 32 WI + 31 reach columns 32 WI .. 32 WI + 31 + 2h).
-// Writes the unnormalised probabilities (bf16 pairs) over the first NPC packed columns of this warp's lanes and returns
-// the row maximum (log2 domain), the row sum and the edge probability of this thread's row.
-template <int WI, int NCH, int NPCH>
-__device__ __forceinline__ void softmax_rows(uint32_t tmem_base, const TcParams& p, int q0, int lane, float t_edge,
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// The softmax of one warp (rows 32 w .. 32 w + 31).  NCH = 32-column chunks of S the warp has to read: its rows reach
+// columns 32 w .. 32 w + 31 + 2h.  Register k of a lane always holds column 32 w + k, so the code is the same for the four
+// warps (only TMEM addresses depend on w): the first version specialised the register indices per warp and ran four
+// 48 KB instruction streams per CTA — 'no instruction' was its dominant stall.
+// Writes the unnormalised probabilities as bf16 pairs: this warp's 16 NCH packed columns at [16 w, 16 w + 16 NCH), zeros
+// over the rest of the NPC = 96 packed columns the second MMA reads; returns the row maximum (log2 domain), the row sum
+// and the edge probability of this thread's row.
+template <int NCH>
+__device__ __forceinline__ void softmax_rows(uint32_t tmem_base, const TcParams& p, int q0, int w, int lane, float t_edge,
                                              float& mx_out, float& sum_out, float& pe_out) {
   float v[NCH * 32];
-  const uint32_t lane_base = tmem_base + ((uint32_t)(WI * 32) << 16);
+  const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     uint32_t r[32];
-    tmem_ld32(lane_base + (uint32_t)(WI * 32 + c * 32), r);
+    tmem_ld32(lane_base + (uint32_t)(w * 32 + c * 32), r);
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(r[i]);
   }
-  const int qi = q0 + WI * 32 + lane;
-  const int jbase = qi - p.h - lane;   // key of register 0 of this lane's band is qi - h = jbase + lane
+  const int qi = q0 + w * 32 + lane;
+  // register k <-> key qi - h + (k - lane): valid iff 0 <= k - lane <= 2h and the key lies in [0, N)
+  const int lo = lane + max(0, p.h - qi);
+  const int hi = lane + min(2 * p.h, p.N - 1 - qi + p.h);
   float mx = t_edge;                    // -inf when this row has no duplicated edge key
 #pragma unroll
   for (int k = 0; k < NCH * 32; ++k) {
-    const int d = k - lane, j = jbase + k;
-    const bool ok = d >= 0 && d <= 2 * p.h && j >= 0 && j < p.N;
+    const bool ok = (unsigned)(k - lo) <= (unsigned)(hi - lo);
     v[k] = ok ? v[k] * p.scale_log2 : -CUDART_INF_F;
     mx = fmaxf(mx, v[k]);
   }
-  if (qi >= p.N) mx = 0.f;              // rows past the sequence: all masked; keep the arithmetic finite
+  if (qi >= p.N || hi < lo) mx = 0.f;   // rows past the sequence: all masked; keep the arithmetic finite
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < NCH * 32; ++k) {
@@ -133,18 +147,21 @@ __device__ __forceinline__ void softmax_rows(uint32_t tmem_base, const TcParams&
   }
   const float pe = ex2f(t_edge - mx);
   sum += pe;
-  // P: packed column pc holds keys (2 pc, 2 pc + 1) of the tile = registers 2 pc - 32 WI and the next one
+  // own columns: registers (2 i, 2 i + 1) -> packed column 16 w + i
 #pragma unroll
-  for (int sc = 0; sc < NPCH; ++sc) {
-    uint32_t r[32];
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t r[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int k = 64 * sc + 2 * i - 32 * WI;
-      const float lo = (k >= 0 && k < NCH * 32) ? v[k >= 0 && k < NCH * 32 ? k : 0] : 0.f;
-      const float hi = (k + 1 >= 0 && k + 1 < NCH * 32) ? v[(k + 1 >= 0 && k + 1 < NCH * 32) ? k + 1 : 0] : 0.f;
-      r[i] = pack_bf16x2(lo, hi);
-    }
-    tmem_st32(lane_base + (uint32_t)(sc * 32), r);
+    for (int i = 0; i < 16; ++i) r[i] = pack_bf16x2(v[c * 32 + 2 * i], v[c * 32 + 2 * i + 1]);
+    tmem_st16(lane_base + (uint32_t)(16 * w + 16 * c), r);
+  }
+  // the rest of the 96 packed columns: zeros (6 - NCH chunks of 16, before and after the warp's own range)
+  {
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+    for (int t = 0; t < 6 - NCH; ++t) tmem_st16(lane_base + (uint32_t)(t < w ? 16 * t : 16 * (t + NCH)), z);
   }
   tmem_wait_st();
   mx_out = mx;
@@ -244,12 +261,7 @@ __global__ void __launch_bounds__(BQ, 2) attn_tc_fwd_kernel(const __grid_constan
   mbar_wait(bar_s, 0);
   tc_fence_after();
   float mx, sum, pe;
-  switch (warp) {
-    case 0: softmax_rows<0, NCH, NPCH>(tmem_base, p, q0, lane, t_edge, mx, sum, pe); break;
-    case 1: softmax_rows<1, NCH, NPCH>(tmem_base, p, q0, lane, t_edge, mx, sum, pe); break;
-    case 2: softmax_rows<2, NCH, NPCH>(tmem_base, p, q0, lane, t_edge, mx, sum, pe); break;
-    default: softmax_rows<3, NCH, NPCH>(tmem_base, p, q0, lane, t_edge, mx, sum, pe); break;
-  }
+  softmax_rows<NCH>(tmem_base, p, q0, warp, lane, t_edge, mx, sum, pe);
   tc_fence_before();
   __syncthreads();   // every lane's P row is in tensor memory
   if (tid == 0) {
@@ -350,7 +362,9 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, void* out, float* l
   if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, BQ)) return rc;
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.KT)) return rc;
   if (int rc = make_map(&tv, v, B, H, N, sb, sn, shh, p.KT)) return rc;
-  const size_t smem = (size_t)(BQ + 2 * p.KT) * 128 + 64 + 4 * 128 + 1024;
+  // at least 78 KB per CTA: two CTAs per SM, which is what tensor memory (2 x 256 columns) allows — a third one would sit
+  // in tcgen05.alloc's retry loop holding shared memory and a barrier's worth of warps
+  const size_t smem = std::max<size_t>((size_t)(BQ + 2 * p.KT) * 128 + 64 + 4 * 128 + 1024, 78 * 1024);
   const int64_t grid = (int64_t)B * H * p.qtiles;
   FAVIT_CHECK_ARG(grid < INT32_MAX, "attn_tc_fwd: grid too large");
   const int nch = (32 + 2 * p.h + 31) / 32;     // S chunks per warp: 2 (W <= 33) or 3
