@@ -33,6 +33,9 @@ bool attn_tc_applicable(int hd, int window, int N, favit_dtype dtype, const uint
                         const void* v, int64_t sb, int64_t sn, int64_t shh);
 int attn_tc_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
                 float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+int attn_tc_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout, void* dq,
+                void* dk, void* dv, float* delta, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
+                int64_t shh, cudaStream_t st);
 int attn_mma_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int hd,
                  int window, float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
 int attn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
@@ -464,6 +467,21 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
     note_kernel("attn_seq_bwd (TMA whole-sequence, mma.sync)");
     return attn_seq_bwd(q, k, v, out, lse, dout, dq, dk, dv, dqkv_colsum, B, H, N, window, scale, stride_b, stride_n,
                         stride_h, (cudaStream_t)stream);
+  }
+  if (!drop && attn_tc_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
+      ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
+      ((uintptr_t)dv % 16) == 0) {
+    note_kernel("attn_tc_bwd (tcgen05 / TMEM: dQ query-major, dK dV key-major, edge rows)");
+    rc = attn_tc_bwd(q, k, v, out, lse, dout, dq, dk, dv, delta, B, H, N, window, scale, stride_b, stride_n, stride_h,
+                     (cudaStream_t)stream);
+    if (rc || !dqkv_colsum) return rc;
+    FAVIT_CHECK_ARG(stride_b == (int64_t)N * stride_n, "mhla_attn_bwd: dqkv_colsum needs batch-contiguous dq/dk/dv");
+    const void* parts_tc[3] = {dq, dk, dv};
+    for (int t = 0; t < 3; ++t) {
+      rc = favit_colsum(parts_tc[t], dtype, dqkv_colsum + (size_t)t * H * hd, B * N, H * hd, stride_n, stream);
+      if (rc) return rc;
+    }
+    return FAVIT_OK;
   }
   if (!drop && attn_mma_applicable(hd, window, dtype, mask)) {
     note_kernel("attn_mma_bwd (per-warp staging, mma.sync)");

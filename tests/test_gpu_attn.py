@@ -162,7 +162,7 @@ def test_module_attention_dropout_statistics():
     assert torch.isfinite(xg.grad).all() and m.latent_proj.weight.grad is not None
 
 
-# wide windows: forward on the tcgen05 / TMEM kernel (mhla_window_attn_tc.cu), backward on the general kernel fed by its LSE
+# wide windows: forward and backward on the tcgen05 / TMEM kernels (mhla_window_attn_tc.cu)
 TC_CASES = [
     # B, H, N, W
     (2, 3, 197, 63),      # C4 tokens, two query tiles, the second one ragged
@@ -179,7 +179,7 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B{}H{}N{}W{}".format(*c))
-def test_wide_window_tcgen05_forward_matches_oracle(case):
+def test_wide_window_tcgen05_forward_backward_match_oracle(case):
     from favit_b200 import _lib as L, ops
     B, H, N, W = case
     hd = 64
@@ -198,11 +198,14 @@ def test_wide_window_tcgen05_forward_matches_oracle(case):
     # every output row is a convex combination of V rows
     vmax = qkv[:, :, 2].float().abs().amax(dim=1).reshape(B, 1, H * hd).cuda()
     assert bool((out.float().abs() <= vmax * 1.01 + 1e-3).all())
-    # the differentiable op: tcgen05 forward + general backward consuming its LSE
+    # backward on the tensor core as well: dQ query-major, dK / dV key-major, the duplicated-edge rows on the CUDA cores
+    dqkv = ops.mhla_attn_bwd(qc.detach(), out, lse, dout.cuda(), W, None)
+    assert L.last_kernel().startswith("attn_tc_bwd"), L.last_kernel()
+    # the differentiable op (autograd runs the same kernels on its own thread)
     out2, _ = ops.mhla_attn(qc, W, None)
     out2.backward(dout.cuda())
     (o_ref * dout.double().cuda()).sum().backward()
-    assert torch.equal(out2, out)
+    assert torch.equal(out2, out) and torch.equal(qc.grad, dqkv)
     scale = q64.grad.abs().max().item()
     for i, nm in enumerate("qkv"):
         assert_close(qc.grad[:, :, i], q64.grad[:, :, i], torch.bfloat16, "d" + nm, factor=2.0, floor=1e-2 * scale)
