@@ -15,6 +15,8 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 // which kernel variant the dispatching entry point chose (favit_last_kernel; tests assert on it)
 void note_kernel(const char* fmt, ...);
+// make the primary context current on this thread (once per thread) before driver-API calls
+void bind_context();
 
 #define FAVIT_CHECK_ARG(cond, ...)                    \
   do {                                                \

@@ -27,6 +27,16 @@ void note_kernel(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Driver-API calls (cuTensorMapEncodeTiled) need a context current on the CALLING thread.  A thread that has only run
+// torch ops served from the caching allocator (autograd's device threads at the start of a backward pass) may not have
+// one yet: cudaSetDevice binds the primary context of the thread's current device, and is legal under stream capture.
+void bind_context() {
+  thread_local bool bound = false;
+  if (bound) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) bound = true;
+}
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int num_sms() {
