@@ -53,6 +53,8 @@ _SIGS = {
     "favit_sppp_pool_attn_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_attn_bwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_pixels": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "favit_slic_grid": ([_i, _i, _i, C.POINTER(_i), C.POINTER(_i)], _i),
+    "favit_slic_segment": ([_vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "favit_adamw_multi": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
                            C.POINTER(_f), C.POINTER(_f), _vp, C.c_double, C.c_double, _f, _f, _vp], _i),
     "favit_sppp_pool_bwd": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),

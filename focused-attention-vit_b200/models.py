@@ -184,15 +184,24 @@ class VisionTransformerMHLA(nn.Module):
 
 
 class SuperpixelSegmentation:
-    """models/sppp.py:26-74: SLIC through scikit-image on the CPU.  Upstream of the hot path (label maps are an input);
-    kept so that the model constructor and `model.segmentation.segment` have the reference's shape."""
+    """models/sppp.py:26-74.  The reference runs SLIC through scikit-image on the CPU, image by image (device -> host
+    copy, Python loop, host -> device copy).  CUDA images are segmented on the device by `favit::slic_segment` for the
+    whole batch at once (same algorithm family; no Lab conversion / connectivity pass, see include/favit.h); CPU images
+    go through scikit-image exactly like the reference, if it is installed."""
 
-    def __init__(self, num_segments: int = 16, compactness: float = 0.1, sigma: float = 1.0):
+    def __init__(self, num_segments: int = 16, compactness: float = 0.1, sigma: float = 1.0, max_num_iter: int = 10):
         self.num_segments = num_segments
         self.compactness = compactness
         self.sigma = sigma
+        self.max_num_iter = max_num_iter     # skimage's default
 
     def segment(self, image: torch.Tensor) -> torch.Tensor:
+        if image.is_cuda:
+            from . import ops
+            batch_mode = image.dim() == 4
+            imgs = image if batch_mode else image.unsqueeze(0)
+            maps = ops.slic_segment(imgs.float(), self.num_segments, self.compactness, self.sigma, self.max_num_iter)
+            return maps if batch_mode else maps[0]
         try:
             from skimage.segmentation import slic
         except ImportError as e:  # not installed in this image

@@ -630,3 +630,41 @@ def _pool_attn_backward(ctx, dout, dw):
 
 
 sppp_pool_attn.register_autograd(_pool_attn_backward, setup_context=_pool_attn_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU SLIC (models/sppp.py:26-74)
+# ------------------------------------------------------------------------------------------------
+def slic_grid(H: int, W: int, n_segments: int) -> Tuple[int, int]:
+    import ctypes as C
+    gy, gx = C.c_int(), C.c_int()
+    L.check(L.lib().favit_slic_grid(H, W, n_segments, C.byref(gy), C.byref(gx)), "favit_slic_grid")
+    return gy.value, gx.value
+
+
+@torch.library.custom_op("favit::slic_segment", mutates_args=())
+def slic_segment(image: Tensor, n_segments: int, compactness: float, sigma: float, iters: int) -> Tensor:
+    """image fp32 [B,C,H,W] (C = 1 or 3) -> int64 [B,H,W] superpixel labels in [0, gy*gx)."""
+    _cuda(image)
+    if image.dtype != torch.float32 or image.dim() != 4:
+        raise ValueError("slic_segment: image must be an fp32 [B,C,H,W] tensor")
+    image = image.contiguous()
+    B, Cc, Hh, Ww = image.shape
+    gy, gx = slic_grid(Hh, Ww, n_segments)
+    K = gy * gx
+    dev = image.device
+    labels = torch.empty((B, Hh, Ww), dtype=torch.int64, device=dev)
+    if labels.numel():
+        feat, tmp = torch.empty_like(image), torch.empty_like(image)
+        centres = torch.empty((B, K, 2 + Cc), dtype=torch.float32, device=dev)
+        sums = torch.empty((B, K, 3 + Cc), dtype=torch.int64, device=dev)
+        work = float(image.numel() * 4) * (4 + 2 * (iters + 1)) + labels.numel() * 8.0 * (iters + 1)
+        rc = L.call("slic", work, L.lib().favit_slic_segment, _p(image), B, Cc, Hh, Ww, n_segments, float(compactness),
+                    float(sigma), int(iters), _p(labels), _p(feat), _p(tmp), _p(centres), _p(sums), _stream())
+        L.check(rc, "favit_slic_segment")
+    return labels
+
+
+@slic_segment.register_fake
+def _(image, n_segments, compactness, sigma, iters):
+    return image.new_empty((image.shape[0], image.shape[2], image.shape[3]), dtype=torch.int64)

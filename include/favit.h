@@ -272,6 +272,22 @@ int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_
                            favit_dtype out_dtype, int R, int r_cap, favit_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GPU superpixel segmentation — replaces the per-image skimage.segmentation.slic call of
+ * models/sppp.py:26-74 (device -> host copy, CPU SLIC, host -> device copy) for the whole batch on the device:
+ * Gaussian pre-smoothing (sigma), gy x gx centres on a regular grid (favit_slic_grid: gx = round(sqrt(n_segments W / H)),
+ * gy = round(n_segments / gx)), `iters` assignment / update rounds with the SLIC distance
+ *   sum_c (f_c - mu_c)^2 / compactness^2 + ((y - cy)^2 + (x - cx)^2) / step^2
+ * over the 3 x 3 grid neighbourhood, centre sums in 64-bit fixed point (deterministic).  labels: int64 [B,H,W] in [0, gy gx).
+ * No Lab conversion and no connectivity enforcement (scikit-image is not installed here: nothing to pin against);
+ * oracle/slic_oracle.py reproduces this function bit for bit.
+ * Workspaces (caller-allocated): feat, tmp fp32 [B,C,H,W]; centres fp32 [B, gy gx, 2 + C]; sums int64 [B, gy gx, 3 + C].
+ * ---------------------------------------------------------------------------------------------- */
+int favit_slic_grid(int H, int W, int n_segments, int* gy, int* gx);
+int favit_slic_segment(const float* image, int B, int C, int H, int W, int n_segments, float compactness, float sigma,
+                       int iters, int64_t* labels, float* feat, float* tmp, float* centres, long long* sums,
+                       favit_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-tensor AdamW — the optimizer.step() of the reference's training loop,
  * experiments/mhla_pretrained.py:320-327,367 (three parameter groups, latent_proj at 5x lr) / main.py:129-132.
  * `count` fp32 tensors, HOST arrays of device pointers / sizes / per-tensor lr and weight decay (a parameter group is

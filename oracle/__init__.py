@@ -31,6 +31,7 @@ from .models_oracle import (  # noqa: F401
     superpixel_centroids,
     dynamic_positional_encoding,
 )
+from .slic_oracle import slic_oracle, slic_grid  # noqa: F401
 from .sppp_oracle import (  # noqa: F401
     map_patches_oracle,
     assign_oracle,
