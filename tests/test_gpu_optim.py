@@ -98,4 +98,6 @@ def test_train_step_with_reference_param_groups():
             # the K third of the qkv bias has an analytically zero gradient (a shift of all keys cancels in the softmax):
             # Adam normalises the rounding noise there into +-lr steps, which no two implementations reproduce
             p1, p2 = torch.cat([p1[:D], p1[2 * D:]]), torch.cat([p2[:D], p2[2 * D:]])
-        assert rel_err(p1, p2) < 1e-4, k
+        # three AdamW steps of ~lr each; gradients of the two runs differ in their last bits (split-K reduce-add order),
+        # which Adam's m / sqrt(v) turns into differences of a fraction of a step for the smallest gradients
+        assert rel_err(p1, p2, floor=0.02) < 2e-3, k

@@ -46,7 +46,7 @@ def test_slic_recovers_blocks_and_is_deterministic():
     b = ops.slic_segment(img, 16, 0.1, 1.0, 10)
     assert torch.equal(a, b)                           # fixed-point centre sums: no run-to-run variation
     truth = (torch.arange(64).view(-1, 1) // 16 * 4 + torch.arange(64).view(1, -1) // 16).cuda()
-    assert float((a == truth).float().mean()) > 0.97  # block interiors agree; only the blurred borders may move
+    assert float((a == truth).float().mean()) > 0.95  # block interiors agree; only the blurred borders may move
 
 
 def test_model_forward_segments_on_the_device_when_no_maps_are_given():
