@@ -17,8 +17,8 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 // bf16 path: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) as a logistic of an odd polynomial,
 //   Phi(x) ~= 1 / (1 + exp(-(c1 x + c3 x^3 + c5 x^5))),   fitted on [-9, 9]:
 //   |Phi error| <= 5.7e-5, |gelu error| <= 2.9e-5 absolute — below bf16 resolution for every |y| >= 0.008, and the
-//   outputs of these epilogues are rounded to bf16 anyway.  2 MUFU + 6 FMA-class instructions per element instead of
-//   erff's ~25: the GELU epilogue has to drain a 128 x 256 tile faster than the tensor pipe fills the next one
+//   outputs of these epilogues are rounded to bf16 anyway.  Round 1 evaluated the logistic with EX2 + RCP (2 MUFU + 6
+//   FMA-class instructions per element instead of erff's ~25); round 2 uses the tanh identity below (1 MUFU): the GELU epilogue has to drain a 128 x 256 tile faster than the tensor pipe fills the next one
 //   (12 k-blocks = 6144 cycles at K = 768), and at 17 instructions per element it did not.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -30,27 +30,37 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// coefficients already multiplied by -log2(e): exp(-k(x)) = 2^(x * poly(x^2)),  Phi(x) ~= sigma(k(x))
-__device__ __forceinline__ float phi_fast(float x) {
-  // the fit is monotone on [-8, 8]; clamping x^2 (one instruction) keeps the exponent monotone beyond: Phi -> 0 / 1
-  const float x2 = fminf(x * x, 64.f);
-  float p = fmaf(1.0319492e-3f, x2, -1.0688557e-1f);
-  p = fmaf(p, x2, -2.3009992f);
-  return rcp_approx(1.f + ex2_approx(p * x));
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+// sigma(k) = 0.5 + 0.5 tanh(k / 2) exactly, so the logistic fit costs ONE special-function instruction (MUFU.TANH)
+// instead of two (EX2 + RCP): the GELU / GELU' epilogues are SFU-bound (a 128 x 256 tile = 64 Ki MUFU at 16 per clock per
+// SM against 6 144 tensor-pipe cycles at K = 768).  Coefficients = those of k(x) / 2:  c1 x + c3 x^3 + c5 x^5 with
+// c1 = 0.79746547 (sqrt(2 / pi) = 0.79788), c3 = 3.7043716e-2, c5 = -3.5764635e-4.  tanh.approx has a relative error of
+// 2^-11: |Phi error| <= 2.5e-4, an order of magnitude below bf16 resolution of the outputs these epilogues store.
+__device__ __forceinline__ float phi_half_arg(float x) {
+  // the fit is monotone on [-8, 8]; clamping x^2 (one instruction) keeps the argument monotone beyond: Phi -> 0 / 1
+  const float x2 = fminf(x * x, 64.f);
+  float p = fmaf(-3.5764635e-4f, x2, 3.7043716e-2f);
+  p = fmaf(p, x2, 0.79746547f);
+  return p * x;
+}
+__device__ __forceinline__ float phi_fast(float x) { return fmaf(0.5f, tanh_approx(phi_half_arg(x)), 0.5f); }
 __device__ __forceinline__ float gelu_fast(float x) { return x * phi_fast(x); }
-// gelu'(x) = Phi(x) + x * phi(x).  With Phi = sigma(k(x)) the density is Phi' = Phi (1 - Phi) k'(x): the exact
-// derivative of gelu_fast, one exponential instead of two (the epilogue is SFU-bound: 3 -> 2 MUFU per element);
-// |error| vs the erf form <= 1.2e-4.  k'(x) = -ln 2 * (5 c5 x^4 + 3 c3 x^2 + c1).
+// gelu'(x) = Phi(x) + x * phi(x).  With Phi = sigma(k(x)) the density is Phi' = Phi (1 - Phi) k'(x) = (1 - t^2) k'(x) / 4,
+// t = tanh(k / 2): the exact derivative of gelu_fast, still one special-function instruction;
+// |error| vs the erf form <= 3e-4.  k'(x) = 2 (c1 + 3 c3 x^2 + 5 c5 x^4).
 __device__ __forceinline__ float dgelu_fast(float x) {
   const float x2 = fminf(x * x, 64.f);
-  float p = fmaf(1.0319492e-3f, x2, -1.0688557e-1f);
-  p = fmaf(p, x2, -2.3009992f);
-  const float P = rcp_approx(1.f + ex2_approx(p * x));
-  float kp = fmaf(-3.5764635e-3f, x2, 2.2226212e-1f);
-  kp = fmaf(kp, x2, 1.5949311f);
-  const float t = fmaf(-P, P, P);  // Phi (1 - Phi): 0 in both tails, where the clamped k' no longer matters
-  return fmaf(x * kp, t, P);
+  float p = fmaf(-3.5764635e-4f, x2, 3.7043716e-2f);
+  p = fmaf(p, x2, 0.79746547f);
+  const float t = tanh_approx(p * x);
+  float kq = fmaf(-8.9411588e-4f, x2, 5.5565574e-2f);   // k'(x) / 4 = (c1 + 3 c3 x^2 + 5 c5 x^4) / 2
+  kq = fmaf(kq, x2, 0.39873274f);
+  const float dens = fmaf(-t, t, 1.f) * kq;             // Phi'(x); 0 in both tails, where the clamped k' no longer matters
+  return fmaf(x, dens, fmaf(0.5f, t, 0.5f));
 }
 
 // ---- MLP dropout (models/vit.py:122,125-139: nn.Dropout after the activation and after fc2) -----------------------------

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--M", type=int, default=256 * 197)
     ap.add_argument("--D", type=int, default=768)
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--once", action="store_true", help="launch every GEMM exactly once (for ncu: one row per GEMM)")
     a = ap.parse_args()
     M, D, Hd = a.M, a.D, 4 * a.D
     bf = torch.bfloat16
@@ -46,6 +47,9 @@ def main():
         fn()
         torch.cuda.synchronize()
         kern = L.last_kernel()
+        if a.once:
+            print(f"{name:26s} {kern}", flush=True)
+            continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.reps):

@@ -26,10 +26,13 @@ def launches(path, out):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         name = re.sub(r"\(.*", "", row["Kernel Name"])
         name = re.sub(r"^void ", "", name)[:100]
         v = float(row["Metric Value"].replace(",", ""))
-        v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
+        u = row["Metric Unit"]
+        v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
         agg[name][0] += 1
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())

@@ -9,7 +9,17 @@ import torch
 
 import favit_b200  # noqa: F401
 from favit_b200 import _lib as L, ops, raw, synth
-from kernel_bench import PEAK_GB, timeit_graph
+from kernel_bench import PEAK_GB, timeit_graph as _timeit_graph
+
+ONCE = "--once" in sys.argv      # for ncu: launch every kernel exactly once instead of timing it
+
+
+def timeit_graph(fn, iters, nbuf):
+    if ONCE:
+        fn(0)
+        torch.cuda.synchronize()
+        return 1.0
+    return _timeit_graph(fn, iters, nbuf)
 
 
 def main():
@@ -20,8 +30,12 @@ def main():
     for (B, N, H, W) in ((15, 4097, 6, 63), (332, 197, 12, 63), (332, 197, 12, 31)):
         D = H * 64
         qkv = [torch.randn(B * N, 3 * D, device=dev).to(bf) for _ in range(3)]
+        do = [torch.randn(B * N, D, device=dev).to(bf) for _ in range(3)]
         t = timeit_graph(lambda i: raw.attn_fwd(qkv[i], B, N, H, 64, W), 8, 3)
         out.append((f"attn fwd N={N} H={H} W={W} [{L.last_kernel().split(' ')[0]}]", t, 4.0 * B * N * D * 2))
+        o, lse = raw.attn_fwd(qkv[0], B, N, H, 64, W) if not ONCE else (torch.empty(B * N, D, device=dev, dtype=bf), torch.zeros(B, H, N, device=dev))
+        t = timeit_graph(lambda i: raw.attn_bwd(qkv[0], o, lse, do[i], B, N, H, 64, W)[0], 4, 3)
+        out.append((f"attn bwd N={N} H={H} W={W} [{L.last_kernel().split(' ')[0]}]", t, 8.0 * B * N * D * 2))
     # SPPP at C2
     B, S, ps, K, D = 256, 224, 16, 16, 384
     lms = [synth.voronoi_label_maps(B, S, K, seed=3 + i, device=dev, exact_k=True, patch_size=ps) for i in range(3)]
