@@ -356,8 +356,8 @@ def sppp_sweep(device, peaks, iters=8):
 
 
 def load_traffic(workload):
-    """Per-launch DRAM bytes of the roofline kernel from the committed ncu capture (profiles/r1_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """Per-launch DRAM bytes of the roofline kernel from the committed ncu capture (profiles/r2_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         return json.load(open(p)).get(workload)
     except Exception:

@@ -49,6 +49,29 @@ void bind_context();
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may become resident while its predecessor in the
+// stream is still running; it must call pdl_wait() before its FIRST global-memory access (reads of what the predecessor
+// wrote, and writes the predecessor may still be reading), and calls pdl_launch_dependents() early so that ITS successor
+// can do the same.  For the 10-15 us SPPP kernels this hides the CTA ramp and the launch gap behind the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

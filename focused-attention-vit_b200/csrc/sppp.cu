@@ -722,13 +722,16 @@ __global__ void __launch_bounds__(kPoolThreads) sppp_pool_fwd_tma_kernel(
     for (int i = tid; i < P; i += kPoolThreads) cp_async4(so + i, order + (int64_t)b * P + i);
     for (int r = tid; r <= R && r <= r_cap; r += kPoolThreads) cp_async4(sf + r, offsets + (int64_t)b * (r_cap + 1) + r);
   };
+  pdl_launch_dependents();
   if (tid == 0) {
     ptx::prefetch_tmap(&tm);
     for (int i = 0; i < stages; ++i) ptx::mbar_init(ptx::smem_u32(&s_bar[i]), 1);
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
-    for (int j = 0; j < stages && j < my_items; ++j) issue(j);
   }
+  pdl_wait();   // everything above is CTA-local set-up; from here on global memory is touched
+  if (tid == 0)
+    for (int j = 0; j < stages && j < my_items; ++j) issue(j);
   fetch_csr(0, 0);
   int ns_next = min(min(num_slots[blockIdx.x / nslices], r_cap), R);
 
@@ -1039,6 +1042,8 @@ __global__ void __launch_bounds__(kBwdRowsThreads) sppp_pool_bwd_rows_kernel(con
   const int tid = threadIdx.x;
   const int b = blockIdx.x / nchunks, ch = blockIdx.x - b * nchunks;
   const int p0 = ch * rows_per_chunk, p1 = min(P, p0 + rows_per_chunk);
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = tid; i < p1 - p0; i += kBwdRowsThreads) {
     const int r = slot[(int64_t)b * P + p0 + i];
     s_slot[i] = (r >= 0 && r < R && r < r_cap) ? r : -1;
@@ -1283,8 +1288,8 @@ int launch_pool_fwd(const void* x, const int32_t* order, const int32_t* offsets,
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
       const int grid = nitems < num_sms() * per_sm ? nitems : num_sms() * per_sm;
       note_kernel("sppp_pool_fwd_tma_kernel grid=%d items=%d stages=%d", grid, nitems, stages);
-      sppp_pool_fwd_tma_kernel<TIn, TOut><<<grid, kPoolThreads, smem, st>>>(
-          tm, order, offsets, num_slots, (TOut*)out, P, R, D, r_cap, nslices, nitems, stages);
+      FAVIT_CHECK_CUDA(launch_pdl(sppp_pool_fwd_tma_kernel<TIn, TOut>, dim3(grid), dim3(kPoolThreads), smem, st, tm, order,
+                                  offsets, num_slots, (TOut*)out, P, R, D, r_cap, nslices, nitems, stages));
       FAVIT_CHECK_LAUNCH();
       return FAVIT_OK;
     }
@@ -1357,8 +1362,8 @@ int launch_pool_bwd(const void* dout, const int32_t* slot, const int32_t* counts
           configured_r = true;
         }
         note_kernel("sppp_pool_bwd_rows_kernel grid=%d rows=%d", B * nchunks, rows);
-        sppp_pool_bwd_rows_kernel<TIn, TOut><<<(unsigned)(B * nchunks), kBwdRowsThreads, smem_r, st>>>(
-            (const TIn*)dout, slot, counts, (TOut*)dx, P, R, D, r_cap, nchunks, rows);
+        FAVIT_CHECK_CUDA(launch_pdl(sppp_pool_bwd_rows_kernel<TIn, TOut>, dim3((unsigned)(B * nchunks)), dim3(kBwdRowsThreads),
+                                    smem_r, st, (const TIn*)dout, slot, counts, (TOut*)dx, P, R, D, r_cap, nchunks, rows));
         FAVIT_CHECK_LAUNCH();
         return FAVIT_OK;
       }
