@@ -159,7 +159,7 @@ def cpu_oracle_step_fn(wl, B):
         loss = torch.nn.functional.cross_entropy(logits, y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     return step, B
 

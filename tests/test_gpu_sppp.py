@@ -312,3 +312,38 @@ def test_assign_with_centroids_in_one_pass_equals_the_two_kernels(B, S, ps, K):
     import oracle
     idx = [0, B - 1]
     assert torch.allclose(got[7][idx].cpu(), oracle.superpixel_centroids(lm[idx].cpu(), K), atol=1e-5)
+
+
+def test_pool_kernels_order_correctly_behind_and_ahead_of_their_neighbours():
+    """The pool kernels are launched with programmatic stream serialization (they may become resident while the previous
+    kernel still runs, and let the next one do the same): every global access must sit behind griddepcontrol.wait.
+    Producer -> pool -> overwrite-the-input chains, back to back, many times; any premature read or write shows up as a
+    mismatch with the result computed from a private copy."""
+    from favit_b200 import ops
+    from favit_b200.sppp import PatchToSuperpixelMapper
+    from favit_b200.synth import voronoi_label_maps
+    B, S, ps, K, D = 64, 224, 16, 16, 384
+    lm = voronoi_label_maps(B, S, K, seed=9, device="cuda", exact_k=True, patch_size=ps)
+    a = PatchToSuperpixelMapper(ps).assign_batch(lm, S, r_cap=K)
+    x = torch.randn(B, 196, D, device="cuda").to(torch.bfloat16)
+    g = torch.randn(B, K, D, device="cuda")
+    outs, refs, dxs, dref = [], [], [], []
+    for i in range(40):
+        x.mul_(1.03).add_(0.01)                            # producer kernels right in front of the pool forward
+        keep = x.clone()
+        outs.append(ops.sppp_pool_fwd(x, a.order, a.offsets, a.num_slots, K, torch.float32))
+        out2 = ops.sppp_pool_fwd(x, a.order, a.offsets, a.num_slots, K, torch.float32)   # pool directly behind pool
+        x.zero_()                                          # a consumer that destroys the input right behind it
+        x.copy_(keep)
+        refs.append((keep, out2))
+        g.mul_(0.99)
+        gk = g.clone()
+        dxs.append(ops.sppp_pool_bwd(g, a.slot, a.counts, torch.bfloat16))
+        g.add_(1.0)                                        # overwrite the backward's input right behind it
+        dref.append(gk)
+        g.copy_(gk)
+    torch.cuda.synchronize()
+    for out, (keep, out2), dx, gk in zip(outs, refs, dxs, dref):
+        ref = ops.sppp_pool_fwd(keep, a.order, a.offsets, a.num_slots, K, torch.float32)
+        assert torch.equal(out, ref) and torch.equal(out2, ref)
+        assert torch.equal(dx, ops.sppp_pool_bwd(gk, a.slot, a.counts, torch.bfloat16))
