@@ -481,7 +481,17 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     prof_ms_step, prof_mode = ms_step, "events around every favit launch of the timed region (eager launches)"
 
     # ---- end to end from pinned host memory (`e2e`) ----
-    host = [tuple(None if t is None else t.cpu().pin_memory() for t in b) for b in batches]
+    # Label maps cross PCIe in the narrowest integer type that holds their labels (K <= 255 superpixels: uint8) and are
+    # widened to the int64 the reference's maps have (sppp.py:64-66) on the device, by the copy into the step's static
+    # input: 12.8 MB per step instead of 102.8 MB at C2.  The images stay fp32, the model's input type.
+    def host_of(t, is_map):
+        if t is None:
+            return None
+        if is_map and args.host_label_dtype != "int64":
+            t = t.to(torch.uint8 if int(t.max()) < 256 else torch.int32)
+        return t.cpu().pin_memory()
+
+    host = [tuple(host_of(t, j == 2) for j, t in enumerate(b)) for b in batches]
     h2d = sum(t.numel() * t.element_size() for t in host[0] if t is not None)
     feeder = HostBatchFeeder(device, 3)
     loss_host = torch.zeros(1, pin_memory=True)
@@ -604,7 +614,8 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
                          % (h2d / 1e6)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 3),
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "host_dtypes": [str(t.dtype).replace("torch.", "") for t in host[0] if t is not None]},
         "gpu_launches": int(launches),
         "loss": {"first_step": round(loss_first, 4), "last_step": round(e2e_losses[-1], 4),
                  "note": "random labels, two alternating batches: the loss falls as AdamW memorises them"},
@@ -637,6 +648,8 @@ def main():
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true",
                     help="capture the training step in a CUDA graph (default)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    ap.add_argument("--host-label-dtype", default="narrow", choices=["narrow", "int64"],
+                    help="e2e: dtype of the label maps in pinned host memory (narrow = uint8 / int32, widened on the device)")
     ap.add_argument("--dp-grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="dtype of the gradients on the wire (bf16 = one flat bf16 buffer, half the NVLink bytes)")
     ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
