@@ -135,3 +135,46 @@ extern "C" int favit_sppp_pool_pixels(const float* image, int B, int C, int img_
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }
+
+// ---- class token + dynamic positional encoding ------------------------------------------------------------------------
+// /root/reference/models/sppp_mhla.py:302-310 and models/sppp.py:271-299: x = cat(cls, pooled); centroids get a (0.5, 0.5)
+// row for the class token; pe = cat(sin(cx * freq), cos(cy * freq)), freq_i = exp(-i ln(10000) / (D/2)); x += pe.
+// One pass instead of eight torch launches (cat, full, arange, exp, mul, sin, cos, cat, add).  out [B, R+1, D] fp32.
+namespace favit {
+namespace {
+__global__ void __launch_bounds__(256) sppp_embed_tokens_kernel(const float* __restrict__ pooled, const float* __restrict__ cls,
+                                                                const float* __restrict__ centroids, float* __restrict__ out,
+                                                                int B, int R, int D) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * (R + 1) * D;
+  if (idx >= total) return;
+  const int d = (int)(idx % D);
+  const int t = (int)((idx / D) % (R + 1));
+  const int b = (int)(idx / ((int64_t)D * (R + 1)));
+  const int half = D / 2;
+  float cx = 0.5f, cy = 0.5f, v;
+  if (t == 0) {
+    v = cls[d];
+  } else {
+    v = pooled[((int64_t)b * R + (t - 1)) * D + d];
+    cx = centroids[((int64_t)b * R + (t - 1)) * 2];
+    cy = centroids[((int64_t)b * R + (t - 1)) * 2 + 1];
+  }
+  const int i = d < half ? d : d - half;
+  const float freq = expf((float)i * (-9.210340371976184f / (float)half));
+  const float pe = d < half ? sinf(cx * freq) : cosf(cy * freq);
+  out[idx] = v + pe;
+}
+}  // namespace
+}  // namespace favit
+
+extern "C" int favit_sppp_embed_tokens(const float* pooled, const float* cls_token, const float* centroids, float* out, int B,
+                                       int R, int D, favit_stream stream) {
+  FAVIT_CHECK_ARG(pooled && cls_token && centroids && out, "sppp_embed_tokens: null pointer");
+  FAVIT_CHECK_ARG(B > 0 && R > 0 && D > 0 && D % 2 == 0, "sppp_embed_tokens: sizes must be > 0 and D even");
+  const int64_t total = (int64_t)B * (R + 1) * D;
+  sppp_embed_tokens_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(pooled, cls_token, centroids, out,
+                                                                                           B, R, D);
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}

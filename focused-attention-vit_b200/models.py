@@ -343,10 +343,17 @@ class SPPPViTMHLA(nn.Module):
             patch_embeddings = self.patch_embed(x)
             pooled = self.pooling.pool_batch(patch_embeddings, assignment, self.num_superpixels,
                                              validate=self.validate_slots)
-        x = torch.cat((self.cls_token.expand(batch_size, -1, -1), pooled), dim=1)
         if centroids is None:
             centroids = self._calculate_superpixel_centroids(segmentation_maps)
-        x = run_blocks(self.blocks, self.pos_embed(x, centroids))
+        if (pooled.is_cuda and pooled.dtype == torch.float32 and self.embed_dim % 2 == 0
+                and centroids.shape[1] == pooled.shape[1]):
+            # class-token concat + dynamic positional encoding (sppp_mhla.py:302-310) in one favit launch
+            from . import ops
+            x = self.pos_embed.dropout(ops.sppp_embed_tokens(pooled, self.cls_token, centroids))
+        else:
+            x = torch.cat((self.cls_token.expand(batch_size, -1, -1), pooled), dim=1)
+            x = self.pos_embed(x, centroids)
+        x = run_blocks(self.blocks, x)
         # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone
         return self.head(self.norm(x[:, 0]))
 

@@ -441,6 +441,42 @@ def _(image, order, offsets, num_slots, patch_size, R, out_dtype):
     return image.new_empty((B, R, patch_size * patch_size * Cc), dtype=out_dtype)
 
 
+@torch.library.custom_op("favit::sppp_embed_tokens", mutates_args=())
+def sppp_embed_tokens(pooled: Tensor, cls_token: Tensor, centroids: Tensor) -> Tensor:
+    """cat(cls, pooled) + dynamic positional encoding of the centroids (sppp_mhla.py:302-310, sppp.py:271-299):
+    pooled fp32 [B,R,D], cls_token [1,1,D] or [D], centroids fp32 [B,R,2] -> fp32 [B,R+1,D]."""
+    _cuda(pooled, cls_token, centroids)
+    pooled = pooled.float().contiguous()
+    cls = cls_token.float().reshape(-1).contiguous()
+    cen = centroids.float().contiguous()
+    B, R, D = pooled.shape
+    if cls.numel() != D or cen.shape != (B, R, 2):
+        raise ValueError(f"sppp_embed_tokens: pooled {tuple(pooled.shape)}, cls {tuple(cls_token.shape)}, centroids {tuple(cen.shape)}")
+    out = torch.empty((B, R + 1, D), dtype=torch.float32, device=pooled.device)
+    if out.numel():
+        rc = L.call("sppp_embed", float(out.numel() * 8), L.lib().favit_sppp_embed_tokens, _p(pooled), _p(cls), _p(cen),
+                    _p(out), B, R, D, _stream())
+        L.check(rc, "favit_sppp_embed_tokens")
+    return out
+
+
+@sppp_embed_tokens.register_fake
+def _(pooled, cls_token, centroids):
+    B, R, D = pooled.shape
+    return pooled.new_empty((B, R + 1, D), dtype=torch.float32)
+
+
+def _embed_setup(ctx, inputs, output):
+    ctx.cls_shape = inputs[1].shape
+
+
+def _embed_backward(ctx, g):
+    return g[:, 1:, :], g[:, 0, :].sum(dim=0).reshape(ctx.cls_shape), None
+
+
+sppp_embed_tokens.register_autograd(_embed_backward, setup_context=_embed_setup)
+
+
 @torch.library.custom_op("favit::sppp_pool_bwd", mutates_args=())
 def sppp_pool_bwd(dout: Tensor, slot: Tensor, counts: Tensor, dx_dtype: torch.dtype) -> Tensor:
     _cuda(dout, slot, counts)

@@ -271,6 +271,13 @@ int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_
                            const int32_t* order, const int32_t* offsets, const int32_t* num_slots, void* out,
                            favit_dtype out_dtype, int R, int r_cap, favit_stream stream);
 
+/* Class-token concat + centroid-based dynamic positional encoding in one pass — replaces models/sppp_mhla.py:302-310 and
+ * models/sppp.py:271-299 (cat, a (0.5, 0.5) centroid row for the class token, pe = cat(sin(cx f), cos(cy f)),
+ * f_i = exp(-i ln(10000) / (D/2)), add).  pooled fp32 [B,R,D], cls_token fp32 [D], centroids fp32 [B,R,2] (x, y);
+ * out fp32 [B,R+1,D].  Gradients are slices of the output gradient (host side). */
+int favit_sppp_embed_tokens(const float* pooled, const float* cls_token, const float* centroids, float* out, int B, int R,
+                            int D, favit_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GPU superpixel segmentation — replaces the per-image skimage.segmentation.slic call of
  * models/sppp.py:26-74 (device -> host copy, CPU SLIC, host -> device copy) for the whole batch on the device:

@@ -347,3 +347,23 @@ def test_pool_kernels_order_correctly_behind_and_ahead_of_their_neighbours():
         ref = ops.sppp_pool_fwd(keep, a.order, a.offsets, a.num_slots, K, torch.float32)
         assert torch.equal(out, ref) and torch.equal(out2, ref)
         assert torch.equal(dx, ops.sppp_pool_bwd(gk, a.slot, a.counts, torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,R,D", [(3, 16, 384), (2, 64, 192), (256, 16, 384), (1, 4, 6)])
+def test_embed_tokens_is_cls_concat_plus_dynamic_positional_encoding(B, R, D):
+    """favit_sppp_embed_tokens against the reference's ops (sppp_mhla.py:302-310 + DynamicPositionalEncoding.forward,
+    sppp.py:271-299), forward and the gradients of the pooled tokens and the class token."""
+    from favit_b200 import ops
+    from favit_b200.models import DynamicPositionalEncoding
+    torch.manual_seed(B + R)
+    pooled = torch.randn(B, R, D, device="cuda", requires_grad=True)
+    cls = torch.randn(1, 1, D, device="cuda", requires_grad=True)
+    cen = torch.rand(B, R, 2, device="cuda")
+    g = torch.randn(B, R + 1, D, device="cuda")
+    out = ops.sppp_embed_tokens(pooled, cls, cen)
+    out.backward(g)
+    p2, c2 = pooled.detach().clone().requires_grad_(True), cls.detach().clone().requires_grad_(True)
+    ref = DynamicPositionalEncoding(D)(torch.cat((c2.expand(B, -1, -1), p2), dim=1), cen)
+    ref.backward(g)
+    assert torch.allclose(out, ref, rtol=0, atol=5e-6)
+    assert torch.allclose(pooled.grad, p2.grad) and torch.allclose(cls.grad, c2.grad, rtol=1e-5, atol=1e-5)
