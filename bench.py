@@ -650,8 +650,10 @@ def main():
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
     ap.add_argument("--host-label-dtype", default="narrow", choices=["narrow", "int64"],
                     help="e2e: dtype of the label maps in pinned host memory (narrow = uint8 / int32, widened on the device)")
-    ap.add_argument("--dp-grad-dtype", default="fp32", choices=["fp32", "bf16"],
-                    help="dtype of the gradients on the wire (bf16 = one flat bf16 buffer, half the NVLink bytes)")
+    ap.add_argument("--dp-grad-dtype", default="bf16", choices=["fp32", "bf16"],
+                    help="dtype of the gradients on the wire under data parallelism (default bf16, the benchmark's compute "
+                         "dtype: one flat bf16 buffer per all-reduce, half the NVLink bytes, fp32 accumulation inside NCCL; "
+                         "fp32 = the gradients travel as they are)")
     ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
                     help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
                          "(default), one collective after backward, or one collective outside the step graph")
