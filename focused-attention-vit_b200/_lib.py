@@ -52,6 +52,7 @@ _SIGS = {
     "favit_sppp_pool_max_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_attn_fwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_attn_bwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_patchify": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "favit_sppp_embed_tokens": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "favit_sppp_pool_pixels": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "favit_slic_grid": ([_i, _i, _i, C.POINTER(_i), C.POINTER(_i)], _i),

@@ -178,3 +178,49 @@ extern "C" int favit_sppp_embed_tokens(const float* pooled, const float* cls_tok
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
 }
+
+// ---- patchify: 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (models/vit.py:38-39) + cast to the GEMM operand type ---------------
+// One pass: fp32 image in, [B*P, p*p*C] rows in the compute dtype out (torch: a permuted fp32 copy, then a cast).
+// Thread -> one output element group of 4 consecutive p2 (so reads are 16-byte, coalesced along image rows); the
+// transposition to the feature order happens through the index arithmetic, writes are 2- / 4-byte strided by C.
+namespace favit {
+namespace {
+template <typename TOut>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, TOut* __restrict__ out, int B, int C,
+                                                       int S, int ps, int g) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B * C * S * S / 4
+  const int64_t total = (int64_t)B * C * S * S / 4;
+  if (idx >= total) return;
+  const int x4 = (int)(idx % (S / 4)) * 4;
+  const int y = (int)((idx / (S / 4)) % S);
+  const int c = (int)((idx / ((int64_t)(S / 4) * S)) % C);
+  const int b = (int)(idx / ((int64_t)(S / 4) * S * C));
+  const float4 v = *reinterpret_cast<const float4*>(img + (((int64_t)b * C + c) * S + y) * S + x4);
+  const int pi = y / ps, p1 = y - pi * ps;
+  const int pj = x4 / ps, p2 = x4 - pj * ps;   // ps % 4 == 0: the four pixels stay inside one patch
+  const int F = ps * ps * C;
+  TOut* o = out + ((int64_t)b * g * g + (int64_t)pi * g + pj) * F + (int64_t)(p1 * ps + p2) * C + c;
+  Elem<TOut>::st(o, v.x);
+  Elem<TOut>::st(o + C, v.y);
+  Elem<TOut>::st(o + 2 * C, v.z);
+  Elem<TOut>::st(o + 3 * C, v.w);
+}
+}  // namespace
+}  // namespace favit
+
+extern "C" int favit_patchify(const float* image, void* out, favit_dtype out_dtype, int B, int C, int S, int patch,
+                              favit_stream stream) {
+  FAVIT_CHECK_ARG(image && out && B > 0 && C > 0 && S > 0 && patch > 0, "patchify: bad argument");
+  FAVIT_CHECK_ARG(S % patch == 0 && patch % 4 == 0 && ((uintptr_t)image % 16 == 0),
+                  "patchify: needs S %% patch == 0, patch %% 4 == 0 and a 16-byte aligned image (S=%d patch=%d)", S, patch);
+  const int64_t total = (int64_t)B * C * S * S / 4;
+  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == FAVIT_BF16)
+    patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(image, (__nv_bfloat16*)out, B, C, S, patch, S / patch);
+  else if (out_dtype == FAVIT_F32)
+    patchify_kernel<float><<<blocks, 256, 0, st>>>(image, (float*)out, B, C, S, patch, S / patch);
+  else { set_error("patchify: bad dtype"); return FAVIT_ERR_ARG; }
+  FAVIT_CHECK_LAUNCH();
+  return FAVIT_OK;
+}

@@ -49,7 +49,29 @@ class PatchEmbedding(nn.Module):
                                         nn.Linear(patch_size * patch_size * in_channels, embed_dim))
 
     def forward(self, x):
+        p = self.patch_size
+        if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and not x.requires_grad and x.shape[2] == x.shape[3]
+                and x.shape[2] % p == 0 and p % 4 == 0):
+            # rearrangement + operand cast in one favit pass, projection on the favit GEMM (fp32 output like nn.Linear
+            # without autocast, the compute dtype under autocast: what the reference's module returns)
+            from . import ops
+            cd = compute_dtype(x)
+            if cd in (torch.float32, torch.bfloat16):
+                lin = self.projection[1]
+                with torch.autocast("cuda", enabled=False):
+                    return ops.linear(ops.patchify(x, p, cd), lin.weight, lin.bias)
         return self.projection(x)
+
+
+def favit_linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """nn.Linear through the favit GEMM (the classification head): same dtypes as nn.Linear with / without autocast."""
+    if x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
+        from . import ops
+        cd = compute_dtype(x)
+        if cd in (torch.float32, torch.bfloat16) and lin.in_features % 8 == 0 and lin.out_features % 8 == 0:
+            with torch.autocast("cuda", enabled=False):
+                return ops.linear(x if x.dtype == cd else x.to(cd), lin.weight, lin.bias)
+    return lin(x)
 
 
 class MLP(nn.Module):
@@ -177,7 +199,7 @@ class VisionTransformerMHLA(nn.Module):
         return self.norm(x[:, 0])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.head(self.forward_features(x))
+        return favit_linear(self.head, self.forward_features(x))
 
     def get_num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -355,7 +377,7 @@ class SPPPViTMHLA(nn.Module):
             x = self.pos_embed(x, centroids)
         x = run_blocks(self.blocks, x)
         # LayerNorm is per token and only the class token is used (sppp_mhla.py:317-323): normalise that row alone
-        return self.head(self.norm(x[:, 0]))
+        return favit_linear(self.head, self.norm(x[:, 0]))
 
     def get_num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

@@ -441,6 +441,31 @@ def _(image, order, offsets, num_slots, patch_size, R, out_dtype):
     return image.new_empty((B, R, patch_size * patch_size * Cc), dtype=out_dtype)
 
 
+@torch.library.custom_op("favit::patchify", mutates_args=())
+def patchify(image: Tensor, patch_size: int, out_dtype: torch.dtype) -> Tensor:
+    """image fp32 [B,C,S,S] -> [B, (S/p)^2, p*p*C] in out_dtype: the rearrangement of models/vit.py:38-39 + the cast to
+    the GEMM operand type in one pass.  No gradient flows to the image."""
+    _cuda(image)
+    if image.dtype != torch.float32 or image.dim() != 4 or image.shape[2] != image.shape[3]:
+        raise ValueError("patchify: image must be a square fp32 [B,C,S,S] tensor")
+    image = image.contiguous()
+    B, Cc, S, _ = image.shape
+    g = S // patch_size
+    out = torch.empty((B, g * g, patch_size * patch_size * Cc), dtype=out_dtype, device=image.device)
+    if out.numel():
+        rc = L.call("patchify", float(image.numel() * 4 + out.numel() * out.element_size()), L.lib().favit_patchify,
+                    _p(image), _p(out), _DT[out_dtype], B, Cc, S, patch_size, _stream())
+        L.check(rc, "favit_patchify")
+    return out
+
+
+@patchify.register_fake
+def _(image, patch_size, out_dtype):
+    B, Cc, S, _ = image.shape
+    g = S // patch_size
+    return image.new_empty((B, g * g, patch_size * patch_size * Cc), dtype=out_dtype)
+
+
 @torch.library.custom_op("favit::sppp_embed_tokens", mutates_args=())
 def sppp_embed_tokens(pooled: Tensor, cls_token: Tensor, centroids: Tensor) -> Tensor:
     """cat(cls, pooled) + dynamic positional encoding of the centroids (sppp_mhla.py:302-310, sppp.py:271-299):

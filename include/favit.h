@@ -278,6 +278,12 @@ int favit_sppp_pool_pixels(const float* image, int B, int C, int img_h, int img_
 int favit_sppp_embed_tokens(const float* pooled, const float* cls_token, const float* centroids, float* out, int B, int R,
                             int D, favit_stream stream);
 
+/* The patch rearrangement of PatchEmbedding (models/vit.py:38-39: einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)') fused
+ * with the cast to the GEMM operand type: image fp32 [B,C,S,S] -> out [B*(S/patch)^2, patch*patch*C] fp32 or bf16, the A
+ * operand of the projection (favit_linear_fwd).  Square images, S % patch == 0, patch % 4 == 0. */
+int favit_patchify(const float* image, void* out, favit_dtype out_dtype, int B, int C, int S, int patch,
+                   favit_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GPU superpixel segmentation — replaces the per-image skimage.segmentation.slic call of
  * models/sppp.py:26-74 (device -> host copy, CPU SLIC, host -> device copy) for the whole batch on the device:

@@ -75,3 +75,45 @@ def test_centroids_match_oracle():
     seg[2][seg[2] == 5] = 99          # a label outside 0..K-1 and an absent label -> (0.5, 0.5)
     got = m._calculate_superpixel_centroids(seg.cuda()).cpu()
     assert torch.allclose(got, oracle.superpixel_centroids(seg, 16), atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,S,ps", [(3, 3, 32, 4), (2, 3, 224, 16), (2, 1, 64, 8), (256, 3, 224, 16)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_patchify_is_the_einops_rearrangement(B, C, S, ps, dtype):
+    """favit_patchify == einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (models/vit.py:38-39) followed by the cast."""
+    from favit_b200 import ops
+    x = torch.randn(B, C, S, S, device="cuda")
+    got = ops.patchify(x, ps, dtype)
+    g = S // ps
+    ref = x.reshape(B, C, g, ps, g, ps).permute(0, 2, 4, 3, 5, 1).reshape(B, g * g, ps * ps * C).to(dtype)
+    assert got.dtype == dtype and torch.equal(got, ref)
+
+
+def test_patch_embedding_and_head_run_on_favit_gemms():
+    """PatchEmbedding.forward and the classification head go through favit::linear (no cuBLAS launch in the step):
+    outputs and weight gradients against nn.Linear on the rearranged patches."""
+    from favit_b200 import _lib as L
+    from favit_b200.models import PatchEmbedding, favit_linear
+    torch.manual_seed(0)
+    pe = PatchEmbedding(img_size=64, patch_size=8, in_channels=3, embed_dim=128).cuda()
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    n0 = L.launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = pe(x)
+    assert L.launch_count() > n0 and y.dtype == torch.bfloat16 and y.shape == (4, 64, 128)
+    y.float().square().sum().backward()
+    lin = pe.projection[1]
+    gw = lin.weight.grad.clone()
+    lin.weight.grad = None
+    patches = x.reshape(4, 3, 8, 8, 8, 8).permute(0, 2, 4, 3, 5, 1).reshape(4, 64, 192)
+    ref = torch.nn.functional.linear(patches.double(), lin.weight.double(), lin.bias.double())
+    assert_close(y, ref, torch.bfloat16, "patch embedding")
+    (ref.float().square().sum()).backward()
+    assert_close(gw, lin.weight.grad, torch.bfloat16, "patch embedding dW", factor=2.0)
+    head = torch.nn.Linear(128, 1000).cuda()
+    t = torch.randn(4, 128, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = favit_linear(head, t)
+    assert out.dtype == torch.bfloat16
+    assert_close(out, torch.nn.functional.linear(t.double(), head.weight.double(), head.bias.double()), torch.bfloat16, "head")
+    assert favit_linear(torch.nn.Linear(128, 10).cuda(), t).shape == (4, 10)      # 10 classes: not a multiple of 8 -> nn.Linear
