@@ -56,6 +56,8 @@ struct K2Params {
   int reduce;    // accumulate into C with TMA reduce-add (split-K or accumulate)
   float* colsum; // [N] fp32, accumulated: column sums of the bf16 output (plain / GELU' epilogues only)
   DropSpec drop; // keep-mask applied after the activation (GELU: to the activation only, not to the saved pre-activation)
+  const float* residual;  // fp32 [M,N] added to an fp32 C (the block's fc2 + residual), row pitch ldres; nullptr = none
+  int64_t ldres;
 };
 
 // this lane's 32-column slice -> its row of a swizzled staging unit (bf16: 4 x 16-byte chunks at chunk offset `c4`)
@@ -265,6 +267,15 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           }
         }
         if (p.drop.seed && p.act != FAVIT_EPI_GELU && !AUX && !p.reduce) dropout32(v, drop_key, row0 + lane, col, p.drop);
+        if (p.residual && p.c_fp32 && !p.reduce && row0 + lane < p.M && col + 32 <= p.N) {
+          // fp32 residual stream: this lane's 32 columns are one 128-byte line of its row
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + (int64_t)(row0 + lane) * p.ldres + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 r4 = __ldg(rp + i);
+            v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+          }
+        }
         if (p.c_fp32) {
           // one staging unit per 32 columns
           uint8_t* ub = outbuf + obuf * kUnit;
@@ -449,7 +460,10 @@ bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t l
   // small problems keep the 1-CTA kernel's narrower tiles; "large" = at least one full wave of 256 x 256 x 512 work
   if (M < 256 || N < 256 || K < 64) return false;
   if ((int64_t)ceil_div(M, 256) * ceil_div(N, 256) * ceil_div(K, 64) < 74 * 8) return false;
-  if (e.residual != nullptr) return false;                          // fp32 residual epilogue stays on the 1-CTA kernel
+  // residual: fp32 into an fp32 C, whole 32-column groups (N % 32 == 0) of 16-byte aligned rows; else the 1-CTA kernel
+  if (e.residual != nullptr && (e.res_dtype != FAVIT_F32 || e.c_dtype != FAVIT_F32 || N % 32 != 0 || e.ldres % 4 != 0 ||
+                                ((uintptr_t)e.residual % 16) != 0 || e.accumulate))
+    return false;
   const int es = e.c_dtype == FAVIT_BF16 ? 2 : 4;
   if (((uintptr_t)e.c % 16) || ((e.ldc * es) % 16)) return false;   // TMA store pitch
   if (e.act == FAVIT_EPI_GELU && (e.c_dtype != FAVIT_BF16 || !e.aux_out || ((uintptr_t)e.aux_out % 16) || ((e.ldaux * 2) % 16)))
@@ -467,7 +481,8 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   const int clusters_max = sms / 2;
   const int m_tiles = ceil_div(M, BM2), n_tiles = ceil_div(N, BN), k_blocks = ceil_div(K, BK);
   const int64_t tiles = (int64_t)m_tiles * n_tiles;
-  const bool can_split = epi.c_dtype == FAVIT_F32 && epi.bias == nullptr && epi.act == FAVIT_EPI_NONE && epi.split_ok;
+  const bool can_split = epi.c_dtype == FAVIT_F32 && epi.bias == nullptr && epi.act == FAVIT_EPI_NONE && epi.split_ok &&
+                         epi.residual == nullptr;
   int splits = 1;
   if (force_splits > 0) {
     splits = force_splits;
@@ -517,9 +532,11 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.reduce = (splits > 1 || epi.accumulate) ? 1 : 0;
   kp.colsum = epi.colsum;
   kp.drop = epi.drop;
+  kp.residual = (const float*)epi.residual;
+  kp.ldres = epi.ldres;
   const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
-  note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d", aux ? 1 : 0,
-              kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn);
+  note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d residual=%d",
+              aux ? 1 : 0, kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn, kp.residual ? 1 : 0);
   return aux ? launch<true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
              : launch<false>(ta, tb, tcm, tc2, taux, kp, clusters, st);
 }

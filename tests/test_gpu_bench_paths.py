@@ -87,15 +87,21 @@ def test_2cta_forward_fp32_out():
 
 
 def test_fc2_forward_with_residual_at_c4():
-    """fc2 + fp32 residual (the block's last GEMM) stays on the single-CTA kernel: checked at the benchmark shape too."""
+    """fc2 + bias + fp32 residual -> fp32 (the block's last GEMM) on the CTA-pair kernel; a ragged N (not a multiple of
+    32) keeps the single-CTA kernel."""
     from favit_b200 import _lib as L, ops
     M, K, N = M4, 3072, 768
     x, w = _bf(M, K, seed=7), _bf(N, K, scale=0.03, seed=8)
     b = torch.randn(N, device="cuda")
     res = torch.randn(M, N, device="cuda")
     y, _ = ops.linear_fwd(x, w, b, res, False, torch.float32, False)
-    assert L.last_kernel().startswith("gemm_bf16_tcgen05_kernel<BN=256>"), L.last_kernel()
+    _ran_2cta(aux=0, act=0, c_fp32=1, reduce=0, residual=1)
     assert rel_err(y, x.double() @ w.double().t() + b.double() + res.double()) < 1e-5
+    N2 = 776
+    w2, b2, res2 = _bf(N2, K, scale=0.03, seed=9), torch.randn(N2, device="cuda"), torch.randn(M, N2, device="cuda")
+    y2, _ = ops.linear_fwd(x, w2, b2, res2, False, torch.float32, False)
+    assert L.last_kernel().startswith("gemm_bf16_tcgen05_kernel<BN=256>"), L.last_kernel()
+    assert rel_err(y2, x.double() @ w2.double().t() + b2.double() + res2.double()) < 1e-5
 
 
 DGRAD = [("c4_fc1", M4, 3072, 768), ("c4_proj", M4, 768, 768), ("c4_qkv", M4, 2304, 768), ("c2_fc1", M2, 1536, 384)]
