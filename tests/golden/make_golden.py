@@ -73,7 +73,9 @@ def gen_module(ref, out):
     # (name, B, N, D, H, W, mask?)
     cases = [("a", 2, 10, 32, 2, 7, False), ("short", 1, 5, 32, 2, 7, False), ("hd64", 2, 17, 64, 1, 7, False),
              ("w3", 1, 12, 48, 3, 3, False), ("mask", 2, 10, 32, 2, 7, True), ("w1", 1, 6, 16, 1, 1, False),
-             ("n1", 2, 1, 32, 2, 7, False), ("w15", 1, 40, 64, 2, 15, False)]
+             ("n1", 2, 1, 32, 2, 7, False), ("w15", 1, 40, 64, 2, 15, False),
+             # wide windows, head_dim 64: the tcgen05 / TMEM attention kernels (round 2)
+             ("w31", 1, 70, 64, 1, 31, False), ("w63", 2, 130, 128, 2, 63, False)]
     names = []
     for name, B, N, D, H, W, use_mask in cases:
         torch.manual_seed(sum(ord(c) for c in name))
