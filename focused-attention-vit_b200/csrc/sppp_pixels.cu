@@ -205,6 +205,40 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   Elem<TOut>::st(o + 2 * C, v.z);
   Elem<TOut>::st(o + 3 * C, v.w);
 }
+
+// C == 3 (every model of the reference): a thread takes four pixels of ALL THREE channel planes (three 16-byte loads) and
+// writes their twelve interleaved features as one contiguous run (24 bytes in bf16, 48 in fp32); consecutive threads write
+// consecutive runs, so both sides of the transposition are coalesced.
+template <typename TOut>
+__global__ void __launch_bounds__(256) patchify3_kernel(const float* __restrict__ img, TOut* __restrict__ out, int B, int S,
+                                                        int ps, int g) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B * S * S / 4
+  const int64_t total = (int64_t)B * S * S / 4;
+  if (idx >= total) return;
+  const int x4 = (int)(idx % (S / 4)) * 4;
+  const int y = (int)((idx / (S / 4)) % S);
+  const int b = (int)(idx / ((int64_t)(S / 4) * S));
+  const int64_t plane = (int64_t)S * S;
+  const float* src = img + (int64_t)b * 3 * plane + (int64_t)y * S + x4;
+  const float4 r = __ldcs(reinterpret_cast<const float4*>(src));
+  const float4 gch = __ldcs(reinterpret_cast<const float4*>(src + plane));
+  const float4 bl = __ldcs(reinterpret_cast<const float4*>(src + 2 * plane));
+  const int pi = y / ps, p1 = y - pi * ps;
+  const int pj = x4 / ps, p2 = x4 - pj * ps;
+  const int F = ps * ps * 3;
+  TOut* o = out + ((int64_t)b * g * g + (int64_t)pi * g + pj) * F + (int64_t)(p1 * ps + p2) * 3;
+  const float f[12] = {r.x, gch.x, bl.x, r.y, gch.y, bl.y, r.z, gch.z, bl.z, r.w, gch.w, bl.w};
+  if constexpr (sizeof(TOut) == 2) {   // 24 bytes, 8-byte aligned (F and 3 * p2 are multiples of 4 elements)
+    uint2* o2 = reinterpret_cast<uint2*>(o);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      o2[i] = make_uint2(pack_bf16x2(f[4 * i], f[4 * i + 1]), pack_bf16x2(f[4 * i + 2], f[4 * i + 3]));
+  } else {
+    float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  }
+}
 }  // namespace
 }  // namespace favit
 
@@ -213,9 +247,18 @@ extern "C" int favit_patchify(const float* image, void* out, favit_dtype out_dty
   FAVIT_CHECK_ARG(image && out && B > 0 && C > 0 && S > 0 && patch > 0, "patchify: bad argument");
   FAVIT_CHECK_ARG(S % patch == 0 && patch % 4 == 0 && ((uintptr_t)image % 16 == 0),
                   "patchify: needs S %% patch == 0, patch %% 4 == 0 and a 16-byte aligned image (S=%d patch=%d)", S, patch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 3 && ((uintptr_t)out % 16 == 0) && (out_dtype == FAVIT_BF16 || out_dtype == FAVIT_F32)) {
+    const unsigned blocks3 = (unsigned)ceil_div64((int64_t)B * S * S / 4, 256);
+    if (out_dtype == FAVIT_BF16)
+      patchify3_kernel<__nv_bfloat16><<<blocks3, 256, 0, st>>>(image, (__nv_bfloat16*)out, B, S, patch, S / patch);
+    else
+      patchify3_kernel<float><<<blocks3, 256, 0, st>>>(image, (float*)out, B, S, patch, S / patch);
+    FAVIT_CHECK_LAUNCH();
+    return FAVIT_OK;
+  }
   const int64_t total = (int64_t)B * C * S * S / 4;
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == FAVIT_BF16)
     patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(image, (__nv_bfloat16*)out, B, C, S, patch, S / patch);
   else if (out_dtype == FAVIT_F32)
