@@ -426,7 +426,7 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
         dist.init_process_group("nccl", device_id=device)
     import favit_b200
     from favit_b200 import _lib as L
-    from favit_b200.engine import HostBatchFeeder, TrainStep
+    from favit_b200.engine import HostBatchFeeder, TrainStep, bind_host_to_gpu
     cc = L.lib().favit_device_cc()
     if cc != 100:
         raise RuntimeError(f"favit_b200 is built for sm_100a only; this device reports compute capability {cc}")
@@ -489,12 +489,19 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
             return None
         if is_map and args.host_label_dtype != "int64":
             t = t.to(torch.uint8 if int(t.max()) < 256 else torch.int32)
-        return t.cpu().pin_memory()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
 
+    # the pinned buffers are allocated with this thread bound to the GPU's own socket (NUMA-local pages: the copy does
+    # not cross the inter-socket link); the previous affinity comes back right after, before any host thread pool starts
+    affinity_before = bind_host_to_gpu(local_rank)
     host = [tuple(host_of(t, j == 2) for j, t in enumerate(b)) for b in batches]
     h2d = sum(t.numel() * t.element_size() for t in host[0] if t is not None)
     feeder = HostBatchFeeder(device, 3)
     loss_ring = torch.zeros(2, pin_memory=True)
+    if affinity_before is not None:
+        os.sched_setaffinity(0, affinity_before)
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_losses = []
 
@@ -512,6 +519,10 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
         loss = step(x, y, maps)
         loss_ring[i % 2:i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
         loss_evs[i % 2].record()
+        if args.e2e_loss_read == "blocking":      # A/B: the reference's `loss.item()` right after the launch
+            loss_evs[i % 2].synchronize()
+            e2e_losses.append(float(loss_ring[i % 2]))
+            return
         if i >= 1:
             loss_evs[(i - 1) % 2].synchronize()
             e2e_losses.append(float(loss_ring[(i - 1) % 2]))
@@ -522,6 +533,17 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     feeder.i = 0
     e2e_ms = timed_steps(e2e_step, args.steps, dist_on, device) / args.steps
     e2e_value = world * B / (e2e_ms / 1e3)
+    # what the host -> device copy of one step's inputs costs alone (the floor of an input-bound e2e step)
+    torch.cuda.synchronize(device)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(feeder.stream):
+        c0.record()
+        for dst, src in zip(feeder.slots[0], host[0]):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        c1.record()
+    torch.cuda.synchronize(device)
+    h2d_alone_ms = c0.elapsed_time(c1)
     # the step must be doing real training: every loss read back is finite and the optimizer has moved it
     import math
     if not (math.isfinite(loss_first) and all(math.isfinite(v) for v in e2e_losses)):
@@ -625,7 +647,10 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
                          % (h2d / 1e6)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms, 3),
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "loss_read": "every step, one step behind the launch",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "loss_read": "every step, one step behind the launch" if args.e2e_loss_read == "lagged" else
+                "every step, blocking right after the launch",
+                "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_alone_gbps": round(h2d / h2d_alone_ms / 1e6, 1),
+                "host_numa_bound": affinity_before is not None,
                 "host_dtypes": [str(t.dtype).replace("torch.", "") for t in host[0] if t is not None]},
         "gpu_launches": int(launches),
         "loss": {"first_step": round(loss_first, 4), "last_step": round(e2e_losses[-1], 4),
@@ -665,6 +690,8 @@ def main():
                     help="dtype of the gradients on the wire under data parallelism (default bf16, the benchmark's compute "
                          "dtype: one flat bf16 buffer per all-reduce, half the NVLink bytes, fp32 accumulation inside NCCL; "
                          "fp32 = the gradients travel as they are)")
+    ap.add_argument("--e2e-loss-read", default="lagged", choices=["lagged", "blocking"],
+                    help="e2e: read each step's loss one step behind the launch (default) or block on it right away")
     ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
                     help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
                          "(default), one collective after backward, or one collective outside the step graph")
