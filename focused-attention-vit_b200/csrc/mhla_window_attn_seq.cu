@@ -36,6 +36,7 @@ struct SeqParams {
   int nbox;        // boxes per operand
   int64_t pairs;   // B * H
   int cs_shared;   // backward: column sums through the CTA's shared-memory accumulator (few heads: few, hot addresses)
+  int ahead;       // CTAs: the operands of CTA blockIdx + ahead are prefetched into L2 while this one computes (0: off)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
@@ -44,6 +45,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
+               "r"(c3)
+               : "memory");
 }
 
 // byte offset of 16-byte chunk `chunk` of row `row` in a 128-byte-row tile with the 128B swizzle (base 1024-aligned)
@@ -112,6 +119,19 @@ __device__ __forceinline__ void issue_loads(const CUtensorMap* const (&tm)[NOPS]
       for (int x = 0; x < p.nbox; ++x)
         tma_load_4d(smem_u32(tiles + g * pair_bytes + t * tile_bytes + (size_t)x * p.rows_box * kRowBytes), tm[t], bar, 0,
                     h, x * p.rows_box, b);
+  }
+  // The CTA that will take this one's place on the SM (blockIdx + the number of resident CTAs) finds its operands in
+  // L2: nobody waits for these reads, so HBM keeps streaming while every resident CTA is in its arithmetic phase.
+  if (p.ahead > 0) {
+    const int64_t next0 = pair0 + (int64_t)p.ahead * p.G;
+    for (int g = 0; g < p.G; ++g) {
+      const int64_t pr = next0 + g;
+      if (pr >= p.pairs) break;
+      const int b = (int)(pr / p.sh.H), h = (int)(pr % p.sh.H);
+#pragma unroll
+      for (int t = 0; t < NOPS; ++t)
+        for (int x = 0; x < p.nbox; ++x) tma_prefetch_4d(tm[t], 0, h, x * p.rows_box, b);
+    }
   }
 }
 
@@ -613,7 +633,24 @@ SeqParams make_params(int B, int H, int N, int window, float scale, int64_t sb, 
   p.G = (int)std::min<int64_t>(G, p.pairs);
   // 3*H*64 global addresses take one reduction per column per warp; measured crossover of the two schemes: H = 6 / 12
   p.cs_shared = H <= 8 ? 1 : 0;
+  p.ahead = 0;
   return p;
+}
+
+// L2 prefetch distance of the forward kernel, in CTAs: half of the CTAs resident at once (measured best of 0 / 0.5 / 1 /
+// 1.5 / 2 x resident at ViT-B, ViT-S and CIFAR shapes: -5 % time; profiles/r2_attn_seq_probe.txt), 0 when the grid fits
+// in one wave.  The backward kernel does not prefetch (same sweep: +3 %; its CTAs wait on arithmetic, not on loads).
+// FAVIT_SEQ_AHEAD = n overrides both (tuning only; n < 0: -n percent of the resident count).
+int prefetch_distance(const void* kernel, int threads, size_t smem, unsigned grid, int default_pct) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  const int resident = occ * num_sms();
+  int ahead = resident * default_pct / 100;
+  if (const char* e = getenv("FAVIT_SEQ_AHEAD")) ahead = atoi(e) < 0 ? resident * -atoi(e) / 100 : atoi(e);
+  return (unsigned)ahead < grid ? ahead : 0;
 }
 
 }  // namespace
@@ -627,7 +664,7 @@ bool attn_seq_applicable(int hd, int window, int N, favit_dtype dtype, const uin
 
 int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
                  float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
-  const SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, nullptr, 3);
+  SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, nullptr, 3);
   CUtensorMap tq, tk, tv;
   if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
@@ -639,6 +676,7 @@ int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* 
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div64(p.pairs, p.G);
+  p.ahead = prefetch_distance((const void*)attn_seq_fwd_kernel<4>, p.G * p.sh.tiles * 32, smem, grid, 50);
   attn_seq_fwd_kernel<4><<<grid, p.G * p.sh.tiles * 32, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)out, lse, p);
   FAVIT_CHECK_LAUNCH();
   return FAVIT_OK;
@@ -647,7 +685,7 @@ int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* 
 int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
                  void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
                  int64_t shh, cudaStream_t st) {
-  const SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, colsum, 4);
+  SeqParams p = make_params(B, H, N, window, scale, sb, sn, shh, colsum, 4);
   CUtensorMap tq, tk, tv, td;
   if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.rows_box)) return rc;
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_box)) return rc;
@@ -661,6 +699,7 @@ int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, con
   }
   const unsigned grid = (unsigned)ceil_div64(p.pairs, p.G);
   const unsigned threads = p.G * p.sh.tiles * 32;
+  p.ahead = prefetch_distance((const void*)attn_seq_bwd_kernel<4>, (int)threads, smem, grid, 0);
   attn_seq_bwd_kernel<4><<<grid, threads, smem, st>>>(tq, tk, tv, td, (const __nv_bfloat16*)o, lse, (__nv_bfloat16*)dq,
                                                       (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
   FAVIT_CHECK_LAUNCH();

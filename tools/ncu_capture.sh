@@ -32,4 +32,28 @@ if hdr:
         w = csv.writer(f); w.writerow(hdr)
         for r in out[:60]: w.writerow(r)
 PY
+# the same samples per CUDA source line (needs -lineinfo, which build.py passes)
+ncu -i ${rep} --page source --csv --print-source cuda 2>/dev/null | head -3000 > /tmp/${name}_cuda_all.csv
+python - <<PY
+import csv
+rows = list(csv.reader(open("/tmp/${name}_cuda_all.csv", errors="replace")))
+hdr, out = None, []
+for r in rows:
+    if hdr is None:
+        if any("Samples" in c for c in r):
+            hdr = r
+        continue
+    out.append(r)
+if hdr:
+    key = [i for i, c in enumerate(hdr) if "Samples" in c][0]
+    def val(r):
+        try: return float(r[key].replace(",", ""))
+        except Exception: return 0.0
+    tot = sum(val(r) for r in out) or 1.0
+    keep = [i for i, c in enumerate(hdr) if c in ("Source", "# Samples", "Instructions Executed", "Warp Stall Sampling (All Samples)") or c.startswith("stall_")]
+    out.sort(key=val, reverse=True)
+    with open("gpurun_out/${name}_cuda_lines.csv", "w") as f:
+        w = csv.writer(f); w.writerow(["share"] + [hdr[i] for i in keep])
+        for r in out[:70]: w.writerow(["%.3f" % (val(r) / tot)] + [r[i] if i < len(r) else "" for i in keep])
+PY
 ls -la gpurun_out/${name}_* | cut -c30-
