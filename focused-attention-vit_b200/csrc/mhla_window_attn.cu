@@ -26,6 +26,14 @@ int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* 
 int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
                  void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
                  int64_t shh, cudaStream_t st);
+// chunked TMA path (mhla_window_attn_chunk.cu): head_dim 64, window <= 15, N > 208 (forward) / N > 400 (backward)
+bool attn_chunk_applicable(int hd, int window, int N, int B, int H, favit_dtype dtype, const uint8_t* mask, const void* q,
+                           const void* k, const void* v, int64_t sb, int64_t sn, int64_t shh, bool backward);
+int attn_chunk_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
+                   float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st);
+int attn_chunk_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
+                   void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
+                   int64_t shh, cudaStream_t st);
 // tensor-core tile path (mhla_window_attn_mma.cu)
 bool attn_mma_applicable(int hd, int window, favit_dtype dtype, const uint8_t* mask);
 // mhla_window_attn_tc.cu: tcgen05 / TMEM forward for wide windows (17 <= W <= 65, head_dim 64, bf16, N >= W)
@@ -423,6 +431,11 @@ extern "C" int favit_mhla_attn_fwd(const void* q, const void* k, const void* v, 
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse, "mhla_attn_fwd: null out/lse");
   const bool drop = dropout_p > 0.f;  // dropout (training, non-default) runs on the general kernels
+  if (!drop && attn_chunk_applicable(hd, window, N, B, H, dtype, mask, q, k, v, stride_b, stride_n, stride_h, false) &&
+      ((uintptr_t)out % 16) == 0) {
+    note_kernel("attn_chunk_fwd (TMA sequence chunks, mma.sync)");
+    return attn_chunk_fwd(q, k, v, out, lse, B, H, N, window, scale, stride_b, stride_n, stride_h, (cudaStream_t)stream);
+  }
   if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
       ((uintptr_t)out % 16) == 0) {
     note_kernel("attn_seq_fwd (TMA whole-sequence, mma.sync)");
@@ -461,6 +474,13 @@ extern "C" int favit_mhla_attn_bwd(const void* q, const void* k, const void* v, 
   if (rc) return rc;
   FAVIT_CHECK_ARG(out && lse && dout && dq && dk && dv && delta, "mhla_attn_bwd: null pointer");
   const bool drop = dropout_p > 0.f;
+  if (!drop && attn_chunk_applicable(hd, window, N, B, H, dtype, mask, q, k, v, stride_b, stride_n, stride_h, true) &&
+      ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
+      ((uintptr_t)dv % 16) == 0) {
+    note_kernel("attn_chunk_bwd (TMA sequence chunks with halo tiles, mma.sync)");
+    return attn_chunk_bwd(q, k, v, out, lse, dout, dq, dk, dv, dqkv_colsum, B, H, N, window, scale, stride_b, stride_n,
+                          stride_h, (cudaStream_t)stream);
+  }
   if (!drop && attn_seq_applicable(hd, window, N, dtype, mask, q, k, v, stride_b, stride_n, stride_h) &&
       ((uintptr_t)dout % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dq % 16) == 0 && ((uintptr_t)dk % 16) == 0 &&
       ((uintptr_t)dv % 16) == 0) {

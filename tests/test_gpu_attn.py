@@ -37,7 +37,7 @@ CASES = [
     (2, 2, 256, 64, 7, False),    # the largest single TMA box
     (1, 2, 300, 64, 7, False),    # two boxes per operand, 19 warps
     (1, 1, 400, 64, 15, False),   # the largest supported sequence, 48 query slots per key tile
-    (1, 2, 401, 64, 7, False),    # one past it: per-warp staging kernels
+    (1, 2, 401, 64, 7, False),    # one past it: the chunked kernels (bf16) / per-warp staging (fp32)
 ]
 
 
@@ -218,3 +218,61 @@ def test_wide_window_gather_oracle_agrees_on_a_small_case():
     a = oracle.mhla_attn_core_gather(q, k, v, 63)
     b, _ = oracle.mhla_attn_core_closed_form(q, k, v, 63)
     assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)
+
+
+# long sequences (N > 208 forward, N > 400 backward) under narrow windows: the chunked TMA kernels (mhla_window_attn_chunk.cu)
+CHUNK_CASES = [
+    # B, H, N, W
+    (1, 2, 401, 7),       # the shortest sequence of this path: three chunks of nine tiles
+    (2, 3, 1025, 7),      # 512-px ViT tokens: six chunks, the last one ragged
+    (1, 12, 1025, 15),    # the widest window; 12 heads: column sums by global reductions
+    (1, 2, 528, 15),      # the sequence ends exactly at a chunk end: the right halo tile is outside the sequence
+    (1, 1, 4097, 3),      # 24 chunks
+    (1, 2, 1024, 1),      # W = 1: no band beyond the diagonal, no duplicated edge keys
+    (1, 1, 705, 7),       # a one-row last tile
+    (2, 1, 417, 5),
+    # 208 < N <= 400: the forward is chunked (the whole-sequence forward would need 14+ warps per CTA), the backward is
+    # still the whole-sequence kernel
+    (2, 3, 209, 7),
+    (1, 2, 257, 15),
+    (1, 12, 400, 7),
+]
+
+
+@pytest.mark.parametrize("case", CHUNK_CASES, ids=lambda c: "B{}H{}N{}W{}".format(*c))
+def test_long_sequence_chunked_forward_backward_match_oracle(case):
+    from favit_b200 import _lib as L, ops, raw
+    B, H, N, W = case
+    hd = 64
+    torch.manual_seed(N + W)
+    qkv = (torch.randn(B, N, 3, H, hd) * 1.5).to(torch.bfloat16)
+    dout = torch.randn(B, N, H * hd).to(torch.bfloat16)
+    qc = qkv.cuda().requires_grad_(True)
+    out, lse = ops.mhla_attn_fwd(qc.detach(), W, None)
+    assert L.last_kernel().startswith("attn_chunk_fwd"), L.last_kernel()
+    q64 = qkv.double().cuda().requires_grad_(True)          # the oracle's closed form, fp64, evaluated on the device
+    q, k, v = [q64[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    o_ref, lse_ref = oracle.mhla_attn_core_closed_form(q, k, v, W, None)
+    o_ref = o_ref.permute(0, 2, 1, 3).reshape(B, N, H * hd)
+    assert_close(out, o_ref, torch.bfloat16, "out")
+    assert_close(lse, lse_ref, torch.bfloat16, "lse")
+    dqkv = ops.mhla_attn_bwd(qc.detach(), out, lse, dout.cuda(), W, None)
+    assert L.last_kernel().startswith("attn_chunk_bwd" if N > 400 else "attn_seq_bwd"), L.last_kernel()
+    out2, _ = ops.mhla_attn(qc, W, None)
+    out2.backward(dout.cuda())
+    (o_ref * dout.double().cuda()).sum().backward()
+    assert torch.equal(out2, out) and torch.equal(qc.grad, dqkv)      # deterministic: no atomics on the data path
+    scale = q64.grad.abs().max().item()
+    for i, nm in enumerate("qkv"):
+        assert_close(qc.grad[:, :, i], q64.grad[:, :, i], torch.bfloat16, "d" + nm, factor=2.0, floor=1e-2 * scale)
+    # the rows next to the sequence ends carry the duplicated-edge terms: check them on their own, tightly scaled
+    h = W // 2
+    if h:
+        for rows in (slice(0, h + 1), slice(N - h - 1, N)):
+            ref = q64.grad[:, rows]
+            assert_close(qc.grad[:, rows], ref, torch.bfloat16, "edge rows", factor=2.0, floor=1e-2 * ref.abs().max().item())
+    # the fused qkv-bias gradient (column sums of the stored bf16 gradient, fp32 atomics across chunks)
+    dqkv2, sums = raw.attn_bwd(qc.detach().reshape(B * N, 3 * H * hd), out, lse, dout.cuda(), B, N, H, hd, W)
+    assert torch.equal(dqkv2.reshape(dqkv.shape), dqkv)
+    want = dqkv.float().sum(dim=(0, 1)).reshape(-1)
+    assert torch.allclose(sums, want, rtol=2e-3, atol=2e-3 * float(want.abs().max()) + 1e-3)

@@ -12,7 +12,11 @@ from kernel_bench import PEAK_GB, timeit_graph
 
 bf = torch.bfloat16
 aheads = sys.argv[1:] or ["0", "-50", "-100", "-200"]
-for (B, N, H, W) in ((256, 197, 12, 7), (256, 197, 6, 7), (1024, 65, 3, 7)):
+SHAPES = ((256, 197, 12, 7), (256, 197, 6, 7), (1024, 65, 3, 7), (63, 1025, 3, 7), (63, 1025, 12, 7), (63, 1025, 12, 15),
+          (15, 4097, 3, 7), (15, 4097, 12, 7))
+if os.environ.get("PROBE_SHAPES"):      # "B,N,H,W;B,N,H,W;..."
+    SHAPES = tuple(tuple(int(x) for x in s.split(",")) for s in os.environ["PROBE_SHAPES"].split(";"))
+for (B, N, H, W) in SHAPES:
     D = H * 64
     qkv = [torch.randn(B * N, 3 * D, device="cuda").to(bf) for _ in range(4)]
     do = [torch.randn(B * N, D, device="cuda").to(bf) for _ in range(4)]
