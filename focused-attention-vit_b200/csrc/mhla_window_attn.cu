@@ -18,7 +18,7 @@
 
 namespace favit {
 
-// whole-sequence TMA path (mhla_window_attn_seq.cu): head_dim 64, N <= 400
+// whole-sequence TMA path (mhla_window_attn_seq.cu): head_dim 64, N <= 400 (the forward only where the chunked one does not apply)
 bool attn_seq_applicable(int hd, int window, int N, favit_dtype dtype, const uint8_t* mask, const void* q, const void* k,
                          const void* v, int64_t sb, int64_t sn, int64_t shh);
 int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
@@ -26,7 +26,7 @@ int attn_seq_fwd(const void* q, const void* k, const void* v, void* out, float* 
 int attn_seq_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
                  void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
                  int64_t shh, cudaStream_t st);
-// chunked TMA path (mhla_window_attn_chunk.cu): head_dim 64, window <= 15, N > 208 (forward) / N > 400 (backward)
+// chunked TMA path (mhla_window_attn_chunk.cu): head_dim 64, window <= 15, N > 48 (forward) / N > 400 (backward)
 bool attn_chunk_applicable(int hd, int window, int N, int B, int H, favit_dtype dtype, const uint8_t* mask, const void* q,
                            const void* k, const void* v, int64_t sb, int64_t sn, int64_t shh, bool backward);
 int attn_chunk_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,

@@ -1,9 +1,10 @@
-// MHLA windowed attention for LONG sequences (N > 400; bf16, head_dim 64, no mask, window <= 15), sm_100a.
+// MHLA windowed attention in sequence CHUNKS (bf16, head_dim 64, no mask, window <= 15; forward N > 48, backward N > 400), sm_100a.
 //
 // Same math and reference span as mhla_window_attn_seq.cu (/root/reference/models/mhla.py:109-154, banded softmax with
 // the duplicated-edge multiplicities of mhla.py:72-79) and the same TMA + mma.sync tile arithmetic; what changes is the
-// unit of work.  A sequence no longer fits in shared memory, so a CTA owns a CHUNK of C = 16 T consecutive rows of one
-// (image, head) sequence (C <= 176, chosen so that the chunks of a sequence are balanced):
+// unit of work.  A CTA owns a CHUNK of C = 16 T consecutive rows of one (image, head) sequence (forward C <= 64, backward
+// C <= 176, chosen so that the chunks of a sequence are balanced) instead of whole sequences: long sequences do not fit
+// in shared memory, and in the forward pass small CTAs hide the load latency better at every length:
 //   forward : Q rows [c0, c0 + C), K / V rows [c0 - 8, c0 + C + 8) (the band never reaches further for W <= 15), one
 //             TMA box per operand — rows before the first / past the last row of the sequence are zero-filled by the
 //             tensor map — plus the two duplicated edge rows (key N-1, key 0), which one warp copies into two spare rows
@@ -30,7 +31,9 @@ namespace {
 using namespace attn;
 using namespace seqk;
 
-constexpr int kMaxChunkTiles = 11;   // 13 warps, 4 x 208 rows x 128 B = 104 KB of tiles in the backward: two CTAs per SM
+constexpr int kMaxChunkTiles = 11;   // backward: 13 warps, 4 x 208 rows x 128 B = 104 KB of tiles, two CTAs per SM
+constexpr int kFwdChunkTiles = 4;    // forward: 64-row chunks, 33 KB of tiles, six CTAs per SM (sweep in profiles/r2_attn_seq_probe.txt:
+                                     // 2 / 3 / 4 / 6 / 8 / 11 tiles -> 0.81 / 0.82 / 0.81 / 0.74 / 0.77 / 0.77 of HBM at ViT-B/16)
 
 struct ChunkParams {
   Shape sh;
@@ -443,9 +446,9 @@ __global__ void __launch_bounds__((kMaxChunkTiles + 2) * 32, 2) attn_chunk_bwd_k
 // host side
 // ---------------------------------------------------------------------------------------------
 ChunkParams make_params(const void* q, const void* k, const void* v, int B, int H, int N, int window, float scale,
-                        int64_t sb, int64_t sn, int64_t shh, float* colsum) {
+                        int64_t sb, int64_t sn, int64_t shh, float* colsum, int max_tiles) {
   ChunkParams p;
-  const int cmax = kMaxChunkTiles * 16;
+  const int cmax = max_tiles * 16;
   p.nchunks = ceil_div(N, cmax);
   p.T = ceil_div(ceil_div(N, p.nchunks), 16);   // balanced chunks
   p.C = p.T * 16;
@@ -463,14 +466,15 @@ ChunkParams make_params(const void* q, const void* k, const void* v, int B, int 
 
 }  // namespace
 
-// Shortest sequence that goes to the chunk kernels: the forward from 14 tiles on (the whole-sequence kernel then runs 14+
-// warps per CTA and, past N = 272, one CTA per SM: measured 5-25 % slower at N = 209 .. 400), the backward past the
-// whole-sequence kernel's limit (in between the two are within +-7 % of each other; profiles/r2_attn_seq_probe.txt).
-// FAVIT_CHUNK_MIN_N overrides both (tuning only).
+// Shortest sequence that goes to the chunk kernels.  Forward: N > 48 — many small CTAs (64-row chunks, six per SM) overlap
+// loads and arithmetic better than one CTA per sequence: 0.82 vs 0.73 of HBM at ViT-B/16 (N 197), 0.75 vs 0.73 at N 65; at
+// N <= 48 the whole-sequence kernel packs several sequences per CTA.  Backward: past the whole-sequence kernel's limit
+// (N > 400): the halo tiles make small chunks expensive (0.43 vs 0.53 at N 197), from N ~ 400 on the two are within
+// +-7 % of each other.  FAVIT_CHUNK_MIN_N / FAVIT_CHUNK_FWD_TILES / FAVIT_CHUNK_BWD_TILES override (tuning only).
 bool attn_chunk_applicable(int hd, int window, int N, int B, int H, favit_dtype dtype, const uint8_t* mask, const void* q,
                            const void* k, const void* v, int64_t sb, int64_t sn, int64_t shh, bool backward) {
   static const int forced = [] { const char* e = getenv("FAVIT_CHUNK_MIN_N"); return e ? std::max(atoi(e), 32) : 0; }();
-  const int min_n = forced ? forced : (backward ? 400 : 208);
+  const int min_n = forced ? forced : (backward ? 400 : 48);
   auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
   return dtype == FAVIT_BF16 && mask == nullptr && hd == HD && window >= 1 && window <= 15 && N > min_n &&
          (int64_t)B * H * ceil_div(N, 16) < INT32_MAX && al(q) && al(k) && al(v) && sb % 8 == 0 && sn % 8 == 0 &&
@@ -479,7 +483,8 @@ bool attn_chunk_applicable(int hd, int window, int N, int B, int H, favit_dtype 
 
 int attn_chunk_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int window,
                    float scale, int64_t sb, int64_t sn, int64_t shh, cudaStream_t st) {
-  const ChunkParams p = make_params(q, k, v, B, H, N, window, scale, sb, sn, shh, nullptr);
+  static const int fwd_tiles = [] { const char* e = getenv("FAVIT_CHUNK_FWD_TILES"); return e ? std::min(std::max(atoi(e), 1), kMaxChunkTiles) : kFwdChunkTiles; }();
+  const ChunkParams p = make_params(q, k, v, B, H, N, window, scale, sb, sn, shh, nullptr, fwd_tiles);
   CUtensorMap tq, tk, tv;
   if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.C)) return rc;
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_kv)) return rc;
@@ -499,7 +504,8 @@ int attn_chunk_fwd(const void* q, const void* k, const void* v, void* out, float
 int attn_chunk_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout, void* dq,
                    void* dk, void* dv, float* colsum, int B, int H, int N, int window, float scale, int64_t sb, int64_t sn,
                    int64_t shh, cudaStream_t st) {
-  const ChunkParams p = make_params(q, k, v, B, H, N, window, scale, sb, sn, shh, colsum);
+  static const int bwd_tiles = [] { const char* e = getenv("FAVIT_CHUNK_BWD_TILES"); return e ? std::min(std::max(atoi(e), 1), kMaxChunkTiles) : kMaxChunkTiles; }();
+  const ChunkParams p = make_params(q, k, v, B, H, N, window, scale, sb, sn, shh, colsum, bwd_tiles);
   CUtensorMap tq, tk, tv, td;
   if (int rc = make_map(&tq, q, B, H, N, sb, sn, shh, p.alloc_rows)) return rc;
   if (int rc = make_map(&tk, k, B, H, N, sb, sn, shh, p.rows_kv)) return rc;

@@ -220,7 +220,7 @@ def test_wide_window_gather_oracle_agrees_on_a_small_case():
     assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)
 
 
-# long sequences (N > 208 forward, N > 400 backward) under narrow windows: the chunked TMA kernels (mhla_window_attn_chunk.cu)
+# the chunked TMA kernels (mhla_window_attn_chunk.cu): forward for N > 48, backward for N > 400, windows <= 15
 CHUNK_CASES = [
     # B, H, N, W
     (1, 2, 401, 7),       # the shortest sequence of this path: three chunks of nine tiles
@@ -231,11 +231,15 @@ CHUNK_CASES = [
     (1, 2, 1024, 1),      # W = 1: no band beyond the diagonal, no duplicated edge keys
     (1, 1, 705, 7),       # a one-row last tile
     (2, 1, 417, 5),
-    # 208 < N <= 400: the forward is chunked (the whole-sequence forward would need 14+ warps per CTA), the backward is
-    # still the whole-sequence kernel
+    # 48 < N <= 400: the forward is chunked (64-row chunks: many small CTAs per SM), the backward is the whole-sequence
+    # kernel
     (2, 3, 209, 7),
     (1, 2, 257, 15),
     (1, 12, 400, 7),
+    (3, 3, 65, 7),        # C1 tokens: two chunks of three tiles, the second one holds one row
+    (1, 12, 197, 7),      # C4 tokens: four chunks
+    (1, 2, 49, 15),       # the shortest sequence of the chunked forward, the widest window: one chunk, both edge keys in it
+    (1, 1, 64, 1),
 ]
 
 
