@@ -436,7 +436,8 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     if wl["kind"] == "sppp":
         model.validate_slots = False          # synthetic maps are validated once, below, not once per step
     step = TrainStep(model, process_group=None, cuda_graph=args.cuda_graph, dp_mode=args.dp_mode,
-                     dp_grad_dtype=torch.bfloat16 if args.dp_grad_dtype == "bf16" else torch.float32)
+                     dp_grad_dtype=torch.bfloat16 if args.dp_grad_dtype == "bf16" else torch.float32,
+                     backward_gemm_tiles=None if args.backward_gemm_tiles == "auto" else args.backward_gemm_tiles)
     # distinct batches so that no step can reuse a cached input; seed differs per rank
     nb = 2
     batches = [make_batch(wl, B, seed=1234 + rank * 100 + i, device=device) for i in range(nb)]
@@ -641,6 +642,7 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
                    "dp_mode": (args.dp_mode + (" (NCCL all-reduce nodes inside the step graph)" if args.cuda_graph and
                                                args.dp_mode != "split" else "")) if dist_on else None,
                    "dp_grad_dtype": args.dp_grad_dtype if dist_on else None,
+                   "backward_gemm_tiles": step.backward_gemm_tiles,
                    "grad_allreduce_calls_per_step": (len(step.reducer.buckets) if args.dp_mode == "overlap" else 1)
                    if dist_on else 0,
                    "l2": "working set >> L2 every step (inputs %.0f MB, activations several GB); no flush needed"
@@ -692,6 +694,9 @@ def main():
                          "fp32 = the gradients travel as they are)")
     ap.add_argument("--e2e-loss-read", default="lagged", choices=["lagged", "blocking"],
                     help="e2e: read each step's loss one step behind the launch (default) or block on it right away")
+    ap.add_argument("--backward-gemm-tiles", default="auto", choices=["auto", "static", "steal"],
+                    help="tile scheduler of the persistent GEMM during backward: 'static' = plain striding (auto), 'steal' = "
+                         "work stealing against SM contention from the overlapped NCCL all-reduce (A/B)")
     ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "deferred", "split", "none"],
                     help="gradient all-reduce under data parallelism: per-bucket collectives overlapped with backward "
                          "(default), one collective after backward, or one collective outside the step graph")

@@ -38,6 +38,7 @@ _SIGS = {
     "favit_dropout_cast": ([_vp, _vp, _i, _vp, _i, _i, _f, _vp, _u64, _vp], _i),
     "favit_linear_wgrad": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp], _i),
     "favit_gemm_bf16_raw": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "favit_set_gemm_tile_scheduler": ([_i], _i),
     "favit_latent_fold_fwd": ([_vp] * 10 + [_i, _i, _i, _vp], _i),
     "favit_latent_fold_bwd": ([_vp] * 11 + [_i, _i, _vp], _i),
     "favit_latent_fold_fwd_batched": ([_i, C.POINTER(_vp), _i, _i, _i, _vp], _i),

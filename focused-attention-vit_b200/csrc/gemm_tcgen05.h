@@ -38,6 +38,10 @@ bool gemm_bf16_2cta_applicable(int M, int N, int K, const Epilogue& e, int64_t l
 int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
                    const Epilogue& epi, int force_splits, cudaStream_t st);
 
+// How the CTA-pair kernel hands out its tiles: 0 = static striding, 1 = work stealing; any other value only queries.
+// Returns the mode in force.
+int gemm_tile_scheduler(int mode);
+
 }  // namespace tc
 
 // fp32 SIMT GEMM (parity path): C[m,n] = sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]

@@ -10,11 +10,27 @@
 // so that global traffic is whole 128-byte lines issued by the TMA unit (and `cp.reduce.async.bulk ... add` replaces
 // per-element atomics for split-K weight gradients).  The GELU' operand is prefetched by TMA loads as well.
 //
-// Cluster of 2 CTAs = one 256 x 256 output tile at a time (persistent, 74 clusters).  Per CTA, 384 threads:
+// Cluster of 2 CTAs = one 256 x 256 output tile at a time (persistent, 74 clusters).  Cluster c owns the units c,
+// c + 74, c + 148, ... (for the training shapes a perfectly balanced schedule, which a greedy global counter is not:
+// measured 34.1 against 30.4 ms per ViT-B step).  Two ways to walk that list, chosen per launch
+// (favit_set_gemm_tile_scheduler):
+//   STEAL = false (default): plain striding, nothing shared.  Fastest when the GPU is ours alone.
+//   STEAL = true: the cluster TAKES its units one at a time through an atomic cursor, and a cluster whose own list is
+//     used up takes units from the lists of other clusters.  A cluster that becomes resident late - because another
+//     kernel (the NCCL all-reduce of data-parallel training) holds some SMs - finds its list already worked off by the
+//     others instead of running it as a second wave after everyone else has gone.  Warp 3 of the leader CTA is the
+//     scheduler: it draws units ahead of the loads and publishes each to every role of both CTAs through a 4-deep
+//     shared-memory ring (st.shared::cluster + mbarriers).  (The producer thread must not do this itself: a
+//     cluster-scope release between two tiles delays the next loads by ~0.6 us, which the 5-stage operand pipeline
+//     does not absorb - measured 32.5 against 30.8 ms per step.)  The last cluster to finish re-arms the cursors, so
+//     launches need no memset.  Costs ~1 % when nothing contends (30.9 against 30.5 ms), hence the switch.
+// Per CTA, 384 threads:
 //   warp 0: TMA producer (its own 128 rows of A and 128 rows of B; bytes are signalled on the LEADER's full barrier)
 //   warp 1: MMA issuer (leader CTA only); tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
 //   warp 2: TMEM allocator (cta_group::2, 512 columns = two 256-column fp32 accumulators)
+//   warp 3: tile scheduler (STEAL only; leader CTA only)
 //   warps 4-11: epilogue; warp w owns TMEM lanes 32*(w%4).. (32 rows) and 128 of the 256 columns.
+#include <atomic>
 #include <mutex>
 
 #include "favit_common.cuh"
@@ -28,6 +44,8 @@ namespace {
 
 using namespace ptx;
 
+std::atomic<int> g_tile_scheduler{0};   // 0 = static striding, 1 = work stealing (favit_set_gemm_tile_scheduler)
+
 constexpr int BMC = 128;   // rows per CTA
 constexpr int BM2 = 256;   // rows per cluster tile
 constexpr int BN = 256;
@@ -39,6 +57,16 @@ constexpr uint32_t kBBytes = (BN / 2) * BK * 2;   // 16 KiB: each CTA stages hal
 constexpr uint32_t kStage = kABytes + kBBytes;
 constexpr uint32_t kSlabBytes = 64 * 128;
 constexpr uint32_t kUnit = 32 * 128;              // one staging unit: 32 rows x 128 bytes
+constexpr int kSched = 4;                         // depth of the tile-index ring
+constexpr int kSchedSlots = 64;                   // sets of global scheduler words, rotated per launch
+constexpr int kSchedWords = 128;                  // per set: one list cursor per cluster (<= 96), kClaimed, kDone
+constexpr int kClaimed = 96;                      // units taken so far, by anyone (a hint: lets thieves skip the scan)
+constexpr int kDone = 97;                         // clusters that have stopped drawing
+// readers of a ring slot: both producers, the leader's MMA issuer, the epilogue warps of both CTAs
+constexpr uint32_t kSchedReaders = 2 + 1 + 2 * kEpiWarps;
+
+// Zero at module load; the last cluster of every launch puts the words it used back to zero.
+__device__ unsigned int g_tile_sched[kSchedSlots][kSchedWords];
 
 template <bool AUX> constexpr int stages() { return AUX ? 4 : 5; }
 template <bool AUX> constexpr int out_bufs() { return AUX ? 1 : 2; }
@@ -58,7 +86,28 @@ struct K2Params {
   DropSpec drop; // keep-mask applied after the activation (GELU: to the activation only, not to the saved pre-activation)
   const float* residual;  // fp32 [M,N] added to an fp32 C (the block's fc2 + residual), row pitch ldres; nullptr = none
   int64_t ldres;
+  int sched_slot;         // which g_tile_sched set this launch draws its tiles from
 };
+
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "st.shared::cluster.u32 [r], %2;\n\t}"
+      ::"r"(addr), "r"(cta), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 // this lane's 32-column slice -> its row of a swizzled staging unit (bf16: 4 x 16-byte chunks at chunk offset `c4`)
 __device__ __forceinline__ void stage_bf16(uint8_t* unit, int lane, int c4, const float (&v)[32]) {
@@ -91,7 +140,7 @@ __device__ __forceinline__ void unstage_bf16(const uint8_t* unit, int lane, int 
   }
 }
 
-template <bool AUX>
+template <bool AUX, bool STEAL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -112,11 +161,23 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   auto aux_bar = [&](int w) { return bar_base + 8u * (2 * S + 4 + w); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4 + kEpiWarps);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  auto sfull_bar = [&](int i) { return tmem_slot + 8u * (1 + i); };            // unit index i of the ring is valid
+  auto sempty_bar = [&](int i) { return tmem_slot + 8u * (1 + kSched + i); };  // (leader's copy) every reader has it
+  auto sched_val = [&](int i) { return tmem_slot + 8u * (1 + 2 * kSched) + 4u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  unsigned int* const sched = g_tile_sched[p.sched_slot];
+
+  const int cluster_id = blockIdx.x >> 1;
+  // units on cluster v's list (v, v + num_clusters, ...); the launch has at most one cluster per unit
+  auto list_len = [&](int v) { return (unsigned int)((total_units - v + num_clusters - 1) / num_clusters); };
+  // the scheduler thread draws from its own list now: the round trip runs under the barrier / TMEM set-up
+  unsigned int drawn = 0;
+  if (STEAL && warp == 3 && lane == 0 && leader) drawn = atomicAdd(sched + cluster_id, 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -135,6 +196,12 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       mbar_init(tempty_bar(a), 2 * kEpiWarps);  // every epilogue warp of both CTAs
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(aux_bar(w), 1);
+    if (STEAL) {
+      for (int i = 0; i < kSched; ++i) {
+        mbar_init(sfull_bar(i), 1);
+        mbar_init(sempty_bar(i), kSchedReaders);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -144,14 +211,41 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_units = p.m_tiles * p.n_tiles * p.splits;
-
+  // Every role asks for its next unit here; >= total_units when there is none.  Static: the cluster's own list by
+  // index.  STEAL: the next entry of the tile ring.
+  int static_u = cluster_id - num_clusters;
+  int sr_slot = 0;
+  uint32_t sr_phase = 0;
+  // Hand-back of a slot after `u` was read from it.  Relaxed arrival (nothing is published, see mbar_arrive_relaxed);
+  // the branch on the loaded value - never negative - keeps the read of the slot ahead of the arrival that lets the
+  // scheduler overwrite it.
+  auto took_unit = [&](int u) {
+    if (lane == 0 && u >= 0) {
+      if (leader) mbar_arrive_relaxed(sempty_bar(sr_slot));
+      else mbar_arrive_cluster_relaxed(sempty_bar(sr_slot), 0);
+    }
+    if (++sr_slot == kSched) { sr_slot = 0; sr_phase ^= 1u; }
+  };
+  // the slot is written by the leader's scheduler: a remote write for the peer CTA (acquire at cluster scope)
+  // `whole_warp`: called by all 32 lanes (epilogue warps) or by lane 0 alone (producer, MMA issuer).
+  auto next_unit = [&](bool whole_warp) -> int {
+    if (!STEAL) {
+      static_u += num_clusters;
+      return static_u < total_units ? static_u : total_units;
+    }
+    if (leader) mbar_wait(sfull_bar(sr_slot), sr_phase);
+    else mbar_wait_cluster(sfull_bar(sr_slot), sr_phase);
+    const int u = (int)ld_shared_u32(sched_val(sr_slot));
+    if (whole_warp) __syncwarp();                      // every lane has read the slot before it is handed back
+    took_unit(u);
+    return u;
+  };
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = cluster_id; u < total_units; u += num_clusters) {
+      for (int u = next_unit(false); u < total_units; u = next_unit(false)) {
         const int tile = u / p.splits, split = u % p.splits;
         const int m0 = (tile / p.n_tiles) * BM2 + (int)rank * BMC;
         const int n0 = (tile % p.n_tiles) * BN + (int)rank * (BN / 2);
@@ -179,6 +273,80 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== tile scheduler (leader CTA only) =====================
+    if (STEAL && leader && lane == 0) {
+      int sw_slot = 0;
+      uint32_t sw_phase = 0;
+      // hand unit `v` to every reader of both CTAs (waits until the slot's previous unit has been read by all of them:
+      // that keeps the scheduler about two tiles ahead of the producers, the ring being 4 deep and the epilogue two
+      // tiles behind the loads)
+      auto publish = [&](int v) {
+        mbar_wait_cluster(sempty_bar(sw_slot), sw_phase ^ 1u);
+        st_shared_cluster_u32(sched_val(sw_slot), 0, (uint32_t)v);
+        st_shared_cluster_u32(sched_val(sw_slot), 1, (uint32_t)v);
+        mbar_arrive_cluster(sfull_bar(sw_slot), 0);
+        mbar_arrive_cluster(sfull_bar(sw_slot), 1);
+        if (++sw_slot == kSched) { sw_slot = 0; sw_phase ^= 1u; }
+      };
+      const unsigned int own_len = list_len(cluster_id);
+      int victim = -1;
+      // a unit from another cluster's list, or total_units when every unit of the launch has been taken
+      auto steal = [&]() -> int {
+        for (;;) {
+          if (victim >= 0) {
+            const unsigned int t = atomicAdd(sched + victim, 1u);
+            if (t < list_len(victim)) {
+              atomicAdd(sched + kClaimed, 1u);
+              return victim + (int)t * num_clusters;
+            }
+            victim = -1;
+          }
+          if (ld_relaxed_gpu(sched + kClaimed) >= (unsigned int)total_units) return total_units;
+          // look at the other clusters' cursors, 16 loads in flight at a time, starting behind this cluster
+          for (int base = 1; base < num_clusters && victim < 0; base += 16) {
+            unsigned int cur[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int v = (cluster_id + base + j) % num_clusters;
+              cur[j] = base + j < num_clusters ? ld_relaxed_gpu(sched + v) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int v = (cluster_id + base + j) % num_clusters;
+              if (victim < 0 && base + j < num_clusters && cur[j] < list_len(v)) victim = v;
+            }
+          }
+          if (victim < 0) return total_units;
+        }
+      };
+      // publish() releases at cluster scope, which waits for this thread's outstanding atomics: the draws for the
+      // NEXT unit are therefore issued after the publish of this one (a draw in flight across the first publish cost
+      // ~2 us at the start of every launch).
+      bool own_left = true;
+      for (;;) {
+        int unit = -1;
+        if (own_left) {
+          if (drawn < own_len) unit = cluster_id + (int)drawn * num_clusters;
+          else own_left = false;
+        }
+        const bool from_own = unit >= 0;
+        if (!from_own) unit = steal();
+        publish(unit);
+        if (unit >= total_units) break;
+        if (from_own) {
+          atomicAdd(sched + kClaimed, 1u);
+          drawn = atomicAdd(sched + cluster_id, 1u);
+        }
+      }
+      // all draws of this cluster are done; the last cluster to get here re-arms the words for the next launch
+      __threadfence();
+      if (atomicAdd(sched + kDone, 1u) == (unsigned int)num_clusters - 1u) {
+        for (int v = 0; v < num_clusters; ++v) sched[v] = 0u;
+        sched[kClaimed] = 0u;
+        sched[kDone] = 0u;
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
@@ -187,7 +355,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = cluster_id; u < total_units; u += num_clusters) {
+      for (int u = next_unit(false); u < total_units; u = next_unit(false)) {
         const int split = u % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
@@ -228,7 +396,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     int obuf = 0;  // next staging buffer (round robin)
-    for (int u = cluster_id; u < total_units; u += num_clusters) {
+    for (int u = next_unit(true); u < total_units; u = next_unit(true)) {
       const int tile = u / p.splits;
       const int row0 = (tile / p.n_tiles) * BM2 + (int)rank * BMC + wq * 32;
       const int col0 = (tile % p.n_tiles) * BN + chalf * 128;
@@ -427,13 +595,13 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int esize, uint64_t inner, uint6
   return FAVIT_OK;
 }
 
-template <bool AUX>
+template <bool AUX, bool STEAL>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tc2,
            const CUtensorMap& taux, const K2Params& kp, int clusters, cudaStream_t st) {
   static bool configured = false;
   constexpr uint32_t smem = smem_bytes<AUX>();
   if (!configured) {
-    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<AUX>,
+    FAVIT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<AUX, STEAL>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
@@ -449,7 +617,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FAVIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<AUX>, ta, tb, tc_, tc2, taux, kp));
+  FAVIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<AUX, STEAL>, ta, tb, tc_, tc2, taux, kp));
   count_launch();
   return FAVIT_OK;
 }
@@ -534,11 +702,25 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.drop = epi.drop;
   kp.residual = (const float*)epi.residual;
   kp.ldres = epi.ldres;
-  const int clusters = (int)min((int64_t)clusters_max, tiles * splits);
-  note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d residual=%d",
-              aux ? 1 : 0, kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn, kp.residual ? 1 : 0);
-  return aux ? launch<true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
-             : launch<false>(ta, tb, tcm, tc2, taux, kp, clusters, st);
+  // Launches that could overlap (different streams, parallel graph branches) must not share a counter pair; a launch
+  // re-arms its pair when it ends, so stream-ordered launches could share one.  64 pairs, round robin.
+  static std::atomic<unsigned int> next_sched_slot{0};
+  const bool steal = g_tile_scheduler.load(std::memory_order_relaxed) == 1;
+  kp.sched_slot = steal ? (int)(next_sched_slot.fetch_add(1u, std::memory_order_relaxed) % kSchedSlots) : 0;
+  const int clusters = (int)min((int64_t)min(clusters_max, kClaimed), tiles * splits);
+  note_kernel("gemm_bf16_tcgen05_2cta_kernel<AUX=%d> act=%d c_fp32=%d reduce=%d splits=%d colsum=%d a_mn=%d b_mn=%d residual=%d steal=%d",
+              aux ? 1 : 0, kp.act, kp.c_fp32, kp.reduce, splits, kp.colsum ? 1 : 0, a_mn, b_mn, kp.residual ? 1 : 0,
+              steal ? 1 : 0);
+  if (steal)
+    return aux ? launch<true, true>(ta, tb, tcm, tc2, taux, kp, clusters, st)
+               : launch<false, true>(ta, tb, tcm, tc2, taux, kp, clusters, st);
+  return aux ? launch<true, false>(ta, tb, tcm, tc2, taux, kp, clusters, st)
+             : launch<false, false>(ta, tb, tcm, tc2, taux, kp, clusters, st);
+}
+
+int gemm_tile_scheduler(int mode) {
+  if (mode == 0 || mode == 1) g_tile_scheduler.store(mode, std::memory_order_relaxed);
+  return g_tile_scheduler.load(std::memory_order_relaxed);
 }
 
 }  // namespace tc

@@ -270,6 +270,8 @@ extern "C" int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const v
   return tc::gemm_bf16(a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, M, N, K, e, bn, splits, (cudaStream_t)stream);
 }
 
+extern "C" int favit_set_gemm_tile_scheduler(int mode) { return tc::gemm_tile_scheduler(mode); }
+
 // ---- many tensors per launch: fp32 master weights -> bf16 GEMM operands, small gradients <-> a flat all-reduce buffer ----
 namespace favit {
 namespace {

@@ -24,7 +24,7 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.05,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, bucket_mb: float = 32.0,
                  optimizer=True, cuda_graph: bool = False, dp_mode: str = "overlap", param_groups=None,
-                 dp_grad_dtype: torch.dtype = torch.float32):
+                 dp_grad_dtype: torch.dtype = torch.float32, backward_gemm_tiles: Optional[str] = None):
         """dp_mode (data parallel only): "overlap" = one coalesced all-reduce per gradient bucket, launched from the
         backward hooks and running beside the rest of backward (also inside the captured graph); "deferred" = one
         coalesced all-reduce of every gradient after backward (inside the graph when cuda_graph); "split" = deferred, with
@@ -39,6 +39,15 @@ class TrainStep:
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb, process_group=process_group,
                                       enabled=False if dp_mode == "none" else None, grad_dtype=dp_grad_dtype)
         self.reducer.overlap = dp_mode == "overlap"
+        # backward_gemm_tiles="steal": the backward GEMMs hand out their tiles by work stealing
+        # (raw.gemm_tile_scheduler), so that a CTA pair which cannot be resident while the overlapped NCCL all-reduce
+        # holds SMs does not run its whole share as a second wave.  Opt-in: at 8 GPUs it measured no better than the
+        # static schedule (33.52 against 33.25 ms per step, profiles/r2_dp.md), and it costs ~1 % on a GPU of our own.
+        if backward_gemm_tiles is None:
+            backward_gemm_tiles = "static"
+        if backward_gemm_tiles not in ("static", "steal"):
+            raise ValueError(f"unknown backward_gemm_tiles {backward_gemm_tiles!r}")
+        self.backward_gemm_tiles = backward_gemm_tiles
         # lr / weight decay: the reference's defaults (main.py:129-132).  optimizer: True / "favit" = the multi-tensor
         # AdamW kernel of this library (optim.FusedAdamW; `param_groups` = e.g. optim.reference_param_groups for the three
         # groups of experiments/mhla_pretrained.py:320-327), "torch" = torch.optim.AdamW(fused=True), False = none
@@ -65,7 +74,15 @@ class TrainStep:
                             enabled=self.autocast_dtype is not None):
             logits = self.model(images) if segmentation_maps is None else self.model(images, segmentation_maps)
         loss = F.cross_entropy(logits.float(), labels)
-        loss.backward()
+        if self.backward_gemm_tiles == "steal":
+            from . import raw
+            raw.gemm_tile_scheduler("steal")        # read at launch (and baked into a captured graph)
+            try:
+                loss.backward()
+            finally:
+                raw.gemm_tile_scheduler("static")
+        else:
+            loss.backward()
         return loss.detach()
 
     def _eager(self, images, labels, segmentation_maps):

@@ -24,6 +24,20 @@ def _p(t: Optional[Tensor]):
 _DROP_STRIDE = 0xD1B54A32D192ED03
 
 
+_TILE_MODES = {"static": 0, "steal": 1}
+
+
+def gemm_tile_scheduler(mode: Optional[str] = None) -> str:
+    """How the persistent CTA-pair GEMM hands out its tiles (include/favit.h: favit_set_gemm_tile_scheduler): "static"
+    striding, or "steal" = work stealing for launches that share the GPU with another kernel (the overlapped NCCL
+    all-reduce).  Process-wide, applies to launches / graph captures made afterwards; None only queries.  Returns the
+    mode in force."""
+    if mode is not None and mode not in _TILE_MODES:
+        raise ValueError(f"unknown tile scheduler {mode!r}: 'static' or 'steal'")
+    got = L.lib().favit_set_gemm_tile_scheduler(-1 if mode is None else _TILE_MODES[mode])
+    return "steal" if got == 1 else "static"
+
+
 def drop_offset(layer: int, site: int) -> int:
     """site 1 = the dropout after the activation, site 2 = the dropout after fc2 (models/vit.py:131-138)."""
     return ((2 * layer + site) * _DROP_STRIDE) & 0xFFFFFFFFFFFFFFFF

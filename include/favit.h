@@ -164,6 +164,15 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
                         int64_t ldc, favit_dtype c_dtype, int M, int N, int K, int bn, int splits,
                         favit_stream stream);
 
+/* How the persistent CTA-pair GEMM (every large Linear of models/mhla.py:100,158 and models/vit.py:107-139) hands its
+ * 256 x 256 tiles to the 74 CTA pairs.  0 (default) = static striding: fastest when the GPU runs nothing else.
+ * 1 = work stealing: a CTA pair that becomes resident late, because another kernel (the NCCL all-reduce of
+ * data-parallel training, which overlaps the backward GEMMs) holds some SMs, finds its tiles taken by the others instead
+ * of running them as a second wave; costs ~1 % without contention.  Takes effect for launches (and graph captures) made
+ * after the call; process-wide.  Any other value only queries.  Returns the mode in force.  No reference counterpart:
+ * the reference is single-process. */
+int favit_set_gemm_tile_scheduler(int mode);
+
 /* ------------------------------------------------------------------------------------------------
  * Latent-projection fold — replaces the two per-token Linear(hd, hd) applications of models/mhla.py:105-106 by a
  * per-step transformation of the qkv / proj WEIGHTS (exact): fwd writes the folded weights in the GEMM

@@ -218,6 +218,84 @@ def test_2cta_repeatable_and_independent_of_previous_tile():
     assert torch.equal(half, first[:M4 // 2])
 
 
+@pytest.fixture
+def steal_tiles():
+    """Work-stealing tile scheduler for the launches of one test (process-wide switch, put back afterwards)."""
+    from favit_b200 import raw
+    assert raw.gemm_tile_scheduler() == "static"
+    raw.gemm_tile_scheduler("steal")
+    yield
+    raw.gemm_tile_scheduler("static")
+
+
+def test_2cta_work_stealing_matches_static_schedule(steal_tiles):
+    """Every epilogue of the CTA-pair kernel with tiles handed out by work stealing (what the backward GEMMs of
+    data-parallel training run): bit-identical to the statically strided launch where every element has one writer
+    (plain bf16, GELU dual store, GELU' AUX), to fp32 summation order where partial tiles are reduce-added (split-K)
+    or column sums are accumulated atomically."""
+    from favit_b200 import ops, raw
+    x, w, b = _bf(M4, 768, seed=40), _bf(3072, 768, scale=0.05, seed=41), torch.randn(3072, device="cuda")
+    dy, w2, pre = _bf(M4, 768, seed=42), _bf(768, 3072, scale=0.05, seed=43), _bf(M4, 3072, scale=1.5, seed=44)
+    xs = _bf(M4, 2304, seed=45)
+
+    def run():
+        y, _ = ops.linear_fwd(x, w, b, None, False, torch.bfloat16, False)
+        k0 = _ran_2cta(aux=0, act=0)
+        g, gpre = ops.linear_fwd(x, w, b, None, True, torch.bfloat16, True)
+        k1 = _ran_2cta(aux=0, act=1)
+        dx, sums = raw.linear_dgrad(dy, w2, pre, torch.bfloat16, colsum=True)
+        k2 = _ran_2cta(aux=1, act=2, colsum=1)
+        dw, db = raw.linear_wgrad(dy, xs, want_bias=True)
+        k3 = _ran_2cta(c_fp32=1, reduce=1)
+        return (y, g, gpre, dx, sums, dw, db), (k0, k1, k2, k3)
+
+    stolen, kernels = run()
+    assert all(" steal=1" in k for k in kernels), kernels
+    for _ in range(3):                      # the cursors re-arm themselves: repeat launches on the same sets
+        again, _ = run()
+        assert all(torch.equal(a, s) for a, s in zip(again[:4], stolen[:4]))
+    raw.gemm_tile_scheduler("static")
+    static, kernels = run()
+    assert all(" steal=0" in k for k in kernels), kernels
+    raw.gemm_tile_scheduler("steal")
+    for name, a, s in zip(("y", "gelu", "pre", "dx"), stolen[:4], static[:4]):
+        assert torch.equal(a, s), name
+    assert rel_err(stolen[4], static[4], floor=1e-3 * float(static[4].abs().max())) < 1e-4     # atomic column sums
+    assert rel_err(stolen[5], static[5]) < 1e-5                                                  # split-K reduce-add
+    assert rel_err(stolen[6], static[6]) < 1e-5
+
+
+def test_2cta_work_stealing_under_sm_contention(steal_tiles):
+    """A launch that finds part of the GPU taken (the NCCL all-reduce of data-parallel training; here: a second
+    persistent GEMM on another stream) still computes every tile exactly once: CTA pairs that become resident late find
+    their lists worked off by the others, or join in.  Interleaved launches on two streams give bit-identical results to
+    the launches run alone, and the cursors re-arm themselves (no memset between launches)."""
+    from favit_b200 import ops
+    x1, w1 = _bf(M4, 768, seed=30), _bf(2304, 768, scale=0.05, seed=31)
+    x2, w2 = _bf(M4 // 2 + 40, 3072, seed=32), _bf(768, 3072, scale=0.03, seed=33)
+    b1, b2 = torch.randn(2304, device="cuda"), torch.randn(768, device="cuda")
+    ref1, _ = ops.linear_fwd(x1, w1, b1, None, False, torch.bfloat16, False)
+    _ran_2cta(steal=1)
+    ref2, _ = ops.linear_fwd(x2, w2, b2, None, False, torch.bfloat16, False)
+    _ran_2cta(steal=1)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for it in range(6):
+        outs1, outs2 = [], []
+        with torch.cuda.stream(s1):
+            for _ in range(4):
+                outs1.append(ops.linear_fwd(x1, w1, b1, None, False, torch.bfloat16, False)[0])
+        with torch.cuda.stream(s2):
+            for _ in range(6):
+                outs2.append(ops.linear_fwd(x2, w2, b2, None, False, torch.bfloat16, False)[0])
+        torch.cuda.synchronize()
+        assert all(torch.equal(o, ref1) for o in outs1), f"stream 1, round {it}"
+        assert all(torch.equal(o, ref2) for o in outs2), f"stream 2, round {it}"
+    # and alone again afterwards: the cursors are back at zero
+    again, _ = ops.linear_fwd(x1, w1, b1, None, False, torch.bfloat16, False)
+    assert torch.equal(again, ref1)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # SPPP pooling at the benchmark's batch sizes
 # ---------------------------------------------------------------------------------------------------------------------
