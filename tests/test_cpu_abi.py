@@ -29,6 +29,21 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(h.favit_launch_count(), int)
 
 
+def test_gemm_tile_scheduler_switch_is_host_state():
+    """favit_set_gemm_tile_scheduler: 0 / 1 set the mode, anything else only queries; the Python wrapper names the modes
+    and refuses unknown ones.  No device needed: the mode is read when a GEMM is launched."""
+    from favit_b200 import _lib, raw
+    h = _lib.lib()
+    assert h.favit_set_gemm_tile_scheduler(-1) == 0            # default: static striding
+    assert h.favit_set_gemm_tile_scheduler(1) == 1
+    assert h.favit_set_gemm_tile_scheduler(7) == 1             # out of range: query only
+    assert raw.gemm_tile_scheduler() == "steal"
+    assert raw.gemm_tile_scheduler("static") == "static"
+    assert h.favit_set_gemm_tile_scheduler(-1) == 0
+    with pytest.raises(ValueError, match="tile scheduler"):
+        raw.gemm_tile_scheduler("dynamic")
+
+
 def test_ops_fail_loudly_without_cuda():
     import torch
     from favit_b200 import ops

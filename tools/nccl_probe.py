@@ -46,7 +46,17 @@ def main():
         f"group of {len(big)} large + 1 flat of the small ones": timeit(lambda: comm.all_reduce_avg(big + [small_flat])),
         "torch.distributed all_reduce flat fp32": timeit(lambda: (dist.all_reduce(flat, op=dist.ReduceOp.AVG), torch.cuda.current_stream().record_event())[1]),
     }
+    flat_b = flat.to(torch.bfloat16)
+    res_b = {
+        "flat bf16 (1 tensor, 173 MB)": timeit(lambda: comm.all_reduce_avg([flat_b])),
+        "one 32 MB-bucket's worth in bf16 (16 MB)": timeit(lambda: comm.all_reduce_avg([flat_b[:8 << 20]])),
+        "12 x 14 MB bf16 back to back": timeit(lambda: [comm.all_reduce_avg([flat_b[i * (7 << 20):(i + 1) * (7 << 20)]])
+                                                        for i in range(12)][-1]),
+    }
     if rank == 0:
+        print(f"world size {dist.get_world_size()}", flush=True)
+        for k, v in res_b.items():
+            print(f"{k:55s} {v:7.3f} ms", flush=True)
         for k, v in res.items():
             print(f"{k:55s} {v:7.3f} ms  {n * 4 / v / 1e6:7.1f} GB/s algbw", flush=True)
     dist.barrier()
