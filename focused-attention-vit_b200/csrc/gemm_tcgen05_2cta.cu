@@ -702,8 +702,9 @@ int gemm_bf16_2cta(const void* A, int a_mn, int64_t lda, const void* B, int b_mn
   kp.drop = epi.drop;
   kp.residual = (const float*)epi.residual;
   kp.ldres = epi.ldres;
-  // Launches that could overlap (different streams, parallel graph branches) must not share a counter pair; a launch
-  // re-arms its pair when it ends, so stream-ordered launches could share one.  64 pairs, round robin.
+  // Launches that could overlap (different streams, parallel graph branches) must not share a set of scheduler words; a
+  // launch re-arms its set when it ends, so stream-ordered launches could share one.  64 sets, round robin: concurrent
+  // launches must be fewer than 64 launches apart, and a captured launch keeps its set (include/favit.h states both).
   static std::atomic<unsigned int> next_sched_slot{0};
   const bool steal = g_tile_scheduler.load(std::memory_order_relaxed) == 1;
   kp.sched_slot = steal ? (int)(next_sched_slot.fetch_add(1u, std::memory_order_relaxed) % kSchedSlots) : 0;

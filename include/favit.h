@@ -170,7 +170,11 @@ int favit_gemm_bf16_raw(const void* a, int a_mn, int64_t lda, const void* b, int
  * data-parallel training, which overlaps the backward GEMMs) holds some SMs, finds its tiles taken by the others instead
  * of running them as a second wave; costs ~1 % without contention.  Takes effect for launches (and graph captures) made
  * after the call; process-wide.  Any other value only queries.  Returns the mode in force.  No reference counterpart:
- * the reference is single-process. */
+ * the reference is single-process.
+ * Limits of mode 1: every launch takes the next of 64 sets of scheduler words (round robin) and re-arms it when it
+ * ends, so launches that RUN CONCURRENTLY must be fewer than 64 launches apart; a launch captured into a CUDA graph
+ * keeps its set, so such a graph must not be replayed concurrently with itself or beside other mode-1 launches on
+ * another stream (stream-ordered use, the training step, is always safe). */
 int favit_set_gemm_tile_scheduler(int mode);
 
 /* ------------------------------------------------------------------------------------------------
