@@ -585,8 +585,9 @@ def run_favit(args, wl, rank, world, local_rank, keep_pg=False):
     g_work, g_ms, g_n = (sum(v[0] for v in gemm), sum(v[1] for v in gemm), sum(v[2] for v in gemm)) if gemm else (0, 1, 0)
     achieved = g_work / (g_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "gemm_bf16_tcgen05_2cta_kernel (+ gemm_bf16_tcgen05_kernel for fc2-with-residual): every GEMM launch of "
-                  "the profiled steps (MHLA qkv / proj and the block's fc1 / fc2; forward, dgrad, wgrad)",
+        "kernel": "gemm_bf16_tcgen05_2cta_kernel (+ the single-CTA gemm_bf16_tcgen05_kernel for the classification head): "
+                  "every GEMM launch of the profiled steps (patch embedding, MHLA qkv / proj, the block's fc1 / fc2, head; "
+                  "forward, dgrad, wgrad)",
         "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
         "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None, "peak_source": peaks["source"] + " (sustained)",
         "launches": g_n, "avg_us_per_launch": round(g_ms * 1e3 / max(g_n, 1), 2), "share_of_step": round(g_ms / prof_total_ms, 4),
